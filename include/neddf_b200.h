@@ -1,0 +1,195 @@
+/*
+ * neddf_b200 -- C ABI of the B200-native NeDDF volumetric-rendering hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (ueda0319/neddf @ f71838ea) is pure Python/PyTorch and has no FFI of its own, so every
+ * entry point below names the reference *function* it replaces (file:line relative to the
+ * reference root).  The Python host classes in neddf_b200/ (NeRFRender, NeDDF) bind
+ * these with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer (fp32 unless stated), row-major,
+ *     contiguous; h_* is a HOST pointer.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls only
+ *     enqueue work; they never synchronise and never allocate caller-visible memory.
+ *   - return value: 0 on success, a negative NEDDF_E_* code on failure;
+ *     neddf_last_error() returns a thread-local message for the last failure.
+ *   - "edges": the reference samples S+1 edge distances per ray; the last one only closes
+ *     the last interval (base_neural_render.py:145-151).
+ */
+#ifndef NEDDF_B200_H
+#define NEDDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEDDF_ABI_VERSION 1
+
+#define NEDDF_OK 0
+#define NEDDF_E_INVALID (-1)     /* bad argument / unsupported configuration */
+#define NEDDF_E_CUDA (-2)        /* CUDA runtime error (message has the detail) */
+#define NEDDF_E_UNSUPPORTED (-3) /* valid reference config this build does not cover */
+
+/* activation ids (neddf/network/neddf.py:95-118) */
+#define NEDDF_ACT_TANHEXP 0
+#define NEDDF_ACT_RELU 1
+#define NEDDF_ACT_LEAKYRELU 2
+
+/* sampling types (neddf/render/nerf_render.py:141-146) */
+#define NEDDF_SAMPLING_POINT 0
+#define NEDDF_SAMPLING_CONE 1
+
+/* uv dtypes accepted by neddf_make_rays (nerf_trainer.py:100-106 uses int16, render_image int64) */
+#define NEDDF_UV_I64 0
+#define NEDDF_UV_I32 1
+#define NEDDF_UV_I16 2
+#define NEDDF_UV_F32 3
+
+/* field engines */
+#define NEDDF_ENGINE_AUTO 0  /* tensor-core path when the configuration allows, else fp32 */
+#define NEDDF_ENGINE_FP32 1  /* CUDA-core fp32 FMA megakernel (bit-faithful fp32 arithmetic) */
+#define NEDDF_ENGINE_TC 2    /* tcgen05 megakernel, 3-product fp16-split operands, fp32 accumulate */
+
+/* output-selection flags for neddf_field_forward* */
+#define NEDDF_OUT_FULL 0      /* everything NeDDF.forward returns, incl. fields_penalty */
+#define NEDDF_OUT_EVAL 1      /* penalty not required: colour-trunk Jacobian rows may be skipped */
+
+#define NEDDF_MAX_SKIPS 8
+#define NEDDF_N_PENALTY 6
+
+/* Constructor arguments of NeDDF (neddf/network/neddf.py:52-66). */
+typedef struct neddf_field_config {
+  int32_t embed_pos_rank;          /* 10 */
+  int32_t embed_dir_rank;          /* 4  */
+  int32_t ddf_layer_count;         /* 8  -> 7 hidden layers + heads */
+  int32_t ddf_layer_width;         /* 256 (only 256 is built) */
+  int32_t col_layer_count;         /* 4  -> 3 hidden layers + head */
+  int32_t col_layer_width;         /* 256 */
+  int32_t activation_type;         /* NEDDF_ACT_* for hidden layers */
+  int32_t density_activation_type; /* NEDDF_ACT_* for the density output */
+  float d_near;
+  int32_t n_skips;
+  int32_t skips[NEDDF_MAX_SKIPS];
+  /* weights in the reference's insertion order (neddf.py:259-300):
+   * constraints_aux_grad, constraints_dDdt, range_distance, range_aux_grad, range_color,
+   * constraints_color; a key absent from the reference dict is passed as 1.0 */
+  float penalty_weight[NEDDF_N_PENALTY];
+} neddf_field_config_t;
+
+/* Warm-up scalars, NeDDF.set_iter (neddf/network/neddf.py:311-326). */
+typedef struct neddf_field_state {
+  float aux_grad_scale;
+  float distance_range_max;
+  float lowpass_alpha;
+} neddf_field_state_t;
+
+typedef struct neddf_field neddf_field_t; /* opaque: config + packed device weights */
+
+int32_t neddf_abi_version(void);
+const char* neddf_last_error(void);
+
+/* Number of linear layers of a configuration and their [in,out] shapes, in the order
+ * layers_ddf.0.., layers_col.0.., layer_ddf_out, layer_aux_out, layer_col_out
+ * (neddf/network/neddf.py:129-145).  shapes_out receives 2*n int32 (may be NULL). */
+int32_t neddf_field_layer_shapes(const neddf_field_config_t* cfg, int32_t* shapes_out, int32_t max_layers);
+
+/* NeDDF.__init__ (neddf.py:52-160): validates the configuration, allocates packed-weight
+ * storage on the current device. */
+int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_field_t** out);
+int32_t neddf_field_destroy(neddf_field_t* f);
+
+/* Re-pack the module's parameters into kernel layout.  d_weights[i] is the i-th layer's
+ * weight, fp32 [in,out] row-major exactly as LinearGradLayer stores it
+ * (nn_module/with_grad/linear.py:111-116); d_biases[i] its bias [out].  Must be called
+ * after load_state_dict / every optimiser step (weights are read when the call is enqueued
+ * on `stream`). */
+int32_t neddf_field_set_weights(neddf_field_t* f, const float* const* d_weights,
+                                const float* const* d_biases, int32_t n_layers, void* stream);
+
+/* Camera.create_rays (neddf/camera/camera.py:155-187, pinhole_calib.py:51-74).
+ * h_R[9] row-major, h_T[3], h_calib = {fx, fy, cx, cy}. */
+int32_t neddf_make_rays(const void* d_uv, int32_t uv_dtype, int64_t n_rays, const float* h_R,
+                        const float* h_T, const float* h_calib, float* d_ray_dir,
+                        float* d_ray_orig, void* stream);
+
+/* Pixel grid of render_image (neddf/render/nerf_render.py:220-230) fused with create_rays for
+ * the row-major pixel range [first, first+n_rays) of a (width/ds) x (height/ds) image. */
+int32_t neddf_make_image_rays(int32_t width, int32_t height, int32_t downsampling, int64_t first,
+                              int64_t n_rays, const float* h_R, const float* h_T,
+                              const float* h_calib, float* d_ray_dir, float* d_ray_orig,
+                              void* stream);
+
+/* Stratified coarse edges: linspace(near,far,n_edges)[j] + u[b,j]*(far-near)/(n_edges-1)
+ * (neddf/render/nerf_render.py:131-139). d_u, d_dists: [n_rays, n_edges]. */
+int32_t neddf_coarse_dists(const float* d_u, int64_t n_rays, int32_t n_edges, float dist_near,
+                           float dist_far, float* d_dists, void* stream);
+
+/* Ray.get_sampling_points / get_sampling_cones (neddf/ray/ray.py:88-194): materialises the
+ * Sampling tensors pos/dir/var [n_rays, n_edges, 3]. */
+int32_t neddf_make_samples(const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
+                           int64_t n_rays, int32_t n_edges, int32_t sampling_type,
+                           float ray_radius, float* d_pos, float* d_dir, float* d_var,
+                           void* stream);
+
+/* NeDDF.forward (neddf/network/neddf.py:162-309) on n samples given as Sampling tensors
+ * pos/dir/var [n,3].  Outputs: distance[n], density[n], color[n,3], penalty[n], aux_grad[n];
+ * any output pointer may be NULL.  `flags` is NEDDF_OUT_*; `engine` NEDDF_ENGINE_*. */
+int32_t neddf_field_forward(const neddf_field_t* f, const neddf_field_state_t* st,
+                            const float* d_pos, const float* d_dir, const float* d_var, int64_t n,
+                            float* d_distance, float* d_density, float* d_color,
+                            float* d_penalty, float* d_aux_grad, int32_t flags, int32_t engine,
+                            void* stream);
+
+/* Same network, with get_sampling_points/cones fused into the prologue: samples are
+ * described by rays + edge distances, nothing of size [n,3] touches HBM. */
+int32_t neddf_field_forward_rays(const neddf_field_t* f, const neddf_field_state_t* st,
+                                 const float* d_ray_dir, const float* d_ray_orig,
+                                 const float* d_dists, int64_t n_rays, int32_t n_edges,
+                                 int32_t sampling_type, float ray_radius, float* d_distance,
+                                 float* d_density, float* d_color, float* d_penalty,
+                                 float* d_aux_grad, int32_t flags, int32_t engine, void* stream);
+
+/* BaseNeuralRender.integrate_volume_render (neddf/render/base_neural_render.py:117-172) plus
+ * the penalty integration of render_rays (nerf_render.py:153-159).
+ * in : dists[n_rays,n_edges], density[n_rays,n_edges], color[n_rays,n_edges,3],
+ *      penalty[n_rays,n_edges] (NULL to skip)
+ * out: weight[n_rays,n_edges-1], depth[n_rays], color_out[n_rays,3], transmittance[n_rays],
+ *      penalty_out[n_rays] (NULL to skip).  d_status (int32, may be NULL) gets bit0 set if a
+ *      NaN weight is produced (the reference asserts, base_neural_render.py:155). */
+int32_t neddf_composite(const float* d_dists, const float* d_density, const float* d_color,
+                        const float* d_penalty, int64_t n_rays, int32_t n_edges, float max_dist,
+                        float* d_weight, float* d_depth, float* d_color_out,
+                        float* d_transmittance, float* d_penalty_out, int32_t* d_status,
+                        void* stream);
+
+/* BaseNeuralRender.sample_pdf with cat_coarse=True (base_neural_render.py:27-115).
+ * in : dists[n_rays,n_edges], weights[n_rays,n_edges-1] (IN/OUT: negative and NaN entries are
+ *      zeroed in place exactly as the reference does to its argument, :52-55), u[n_rays,n_new]
+ * out: dists_fine[n_rays, n_edges+n_new] sorted; optional ids[n_rays,n_new] (int64,
+ *      searchsorted right=True) and cdf[n_rays,n_edges].  The batch-wide NaN fallback
+ *      (base_neural_render.py:105-114) is applied on device; d_status bit1 records it. */
+int32_t neddf_sample_pdf(const float* d_dists, float* d_weights, const float* d_u,
+                         int64_t n_rays, int32_t n_edges, int32_t n_new, float* d_dists_fine,
+                         int64_t* d_ids, float* d_cdf, int32_t* d_status, void* stream);
+
+/* The inverse-CDF step alone on a caller-supplied cdf (base_neural_render.py:77-98); used to
+ * check sample indices bit-exactly against torch.searchsorted. */
+int32_t neddf_invert_cdf(const float* d_dists, const float* d_cdf, const float* d_u,
+                         int64_t n_rays, int32_t n_edges, int32_t n_new, float* d_samples,
+                         int64_t* d_ids, void* stream);
+
+/* How many kernels this library has launched since load (bench.py "gpu_launches"). */
+int64_t neddf_launch_count(void);
+
+/* Self-test of the tcgen05 GEMM building block: C[M,N] = A[M,K] * B[N,K]^T with fp16-split
+ * operands; returns 0 and fills d_c.  Used by tests to pin the UMMA descriptor layouts. */
+int32_t neddf_tc_selftest(const float* d_a, const float* d_b, int32_t m, int32_t n, int32_t k,
+                          float* d_c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEDDF_B200_H */
