@@ -1,0 +1,273 @@
+"""NeDDF field network: the reference's module surface over the CUDA megakernel.
+
+Reference: neddf/network/neddf.py (NeDDF), neddf/network/base_neuralfield.py
+(BaseNeuralField), neddf/nn_module/with_grad/linear.py:87-133 (LinearGradLayer parameters).
+
+The module owns the same parameters under the same names/shapes as the reference
+(``layers_ddf.{i}.weight`` [in,out] ...), so ``state_dict`` files are interchangeable.  All
+arithmetic of ``forward`` happens in libneddf_b200.so (neddf_field_forward*); the parameters
+are re-packed into kernel layout whenever their version counters change (optimiser steps
+update them in place).
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import _lib as L
+from .ray import Sampling
+
+
+class LinearGradLayer(nn.Module):
+    """Parameter holder with the reference's layout: weight [in,out] xavier-normal, zero bias
+    (nn_module/with_grad/linear.py:111-116).  The product computes y = xW + b, G = JW inside
+    the fused field kernel, never layer by layer."""
+
+    def __init__(self, input_ch: int = 128, output_ch: int = 128) -> None:
+        super().__init__()
+        self.input_ch, self.output_ch = input_ch, output_ch
+        self.weight = nn.Parameter(torch.randn(input_ch, output_ch))
+        self.bias = nn.Parameter(torch.randn(output_ch))
+        nn.init.xavier_normal_(self.weight)
+        nn.init.constant_(self.bias, 0.0)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise NotImplementedError("neddf_b200 fuses all linear layers into the field megakernel; "
+                                  "call NeDDF.forward instead")
+
+
+class BaseNeuralField(nn.Module):
+    """neddf/network/base_neuralfield.py:11-79."""
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    def set_iter(self, iter: int) -> None:
+        pass
+
+    def voxelize(self, field_name: str = "density", cube_range: float = 1.1, cube_resolution: int = 64,
+                 chunk: int = 65536) -> np.ndarray:
+        """Dense-grid evaluation (base_neuralfield.py:49-79); same point order as the reference."""
+        with torch.set_grad_enabled(False):
+            ids = np.linspace(-cube_range, cube_range, cube_resolution)
+            zs, ys, xs = np.meshgrid(ids, ids, ids)
+            pos = torch.from_numpy(np.stack([xs.reshape(-1), ys.reshape(-1), zs.reshape(-1)], 1).astype(np.float32))
+            n = cube_resolution ** 3
+            device = self.device
+            result = np.zeros(n, np.float32)
+            one_dir = torch.tensor([[1.0, 0.0, 0.0]])
+            for i in range(0, n, chunk):
+                j = min(n, i + chunk)
+                p = pos[None, i:j, :].to(device)
+                s = Sampling(p, one_dir.expand(j - i, -1)[None].to(device).contiguous(), torch.zeros_like(p))
+                result[i:j] = self.forward(s)[field_name].view(-1).detach().cpu().numpy()
+            return result.reshape(cube_resolution, cube_resolution, cube_resolution)
+
+
+class NeDDF(BaseNeuralField):
+    """Drop-in for neddf.network.NeDDF (neddf/network/neddf.py:21-326)."""
+
+    def __init__(
+        self,
+        embed_pos_rank: int = 10,
+        embed_dir_rank: int = 4,
+        ddf_layer_count: int = 8,
+        ddf_layer_width: int = 256,
+        col_layer_count: int = 8,
+        col_layer_width: int = 256,
+        activation_type: str = "tanhExp",
+        density_activation_type: str = "ReLU",
+        d_near: float = 0.01,
+        lowpass_alpha_offset: float = 10.0,
+        skips: Optional[List[int]] = None,
+        penalty_weight: Optional[Dict[str, float]] = None,
+    ) -> None:
+        super().__init__()
+        input_ddf_dim = embed_pos_rank * 6
+        input_col_dim = (embed_pos_rank + embed_dir_rank) * 6 + 3 + ddf_layer_width
+        if skips is None:
+            skips = [4]
+        self.skips = [int(s) for s in skips]
+        if activation_type not in L.ACT_IDS or density_activation_type not in L.ACT_IDS:
+            raise KeyError(f"unknown activation {activation_type!r}/{density_activation_type!r}")  # neddf.py:107-118
+        self.activation_type = activation_type
+        self.density_activation_type = density_activation_type
+        self.embed_pos_rank, self.embed_dir_rank = int(embed_pos_rank), int(embed_dir_rank)
+        self.ddf_layer_count, self.col_layer_count = int(ddf_layer_count), int(col_layer_count)
+        self.ddf_layer_width, self.col_layer_width = int(ddf_layer_width), int(col_layer_width)
+
+        # identical construction order and shapes to neddf.py:129-145
+        layers_ddf = [LinearGradLayer(input_ddf_dim, ddf_layer_width)]
+        for layer_id in range(ddf_layer_count - 2):
+            extra = input_ddf_dim if layer_id in self.skips else 0
+            layers_ddf.append(LinearGradLayer(ddf_layer_width + extra, ddf_layer_width))
+        layers_col = [LinearGradLayer(input_col_dim, col_layer_width)]
+        for _ in range(col_layer_count - 2):
+            layers_col.append(LinearGradLayer(col_layer_width, col_layer_width))
+        self.layers_ddf = nn.ModuleList(layers_ddf)
+        self.layers_col = nn.ModuleList(layers_col)
+        self.layer_ddf_out = LinearGradLayer(ddf_layer_width, 1)
+        self.layer_aux_out = LinearGradLayer(ddf_layer_width, 1)
+        self.layer_col_out = LinearGradLayer(ddf_layer_width, 3)
+
+        self.d_near = float(d_near)
+        self.aux_grad_scale = 1.1
+        self.distance_range_max = 2.0
+        self.lowpass_alpha_offset = float(lowpass_alpha_offset)
+        self.lowpass_alpha = float(lowpass_alpha_offset)
+        if penalty_weight is None:
+            penalty_weight = {"constraints_aux_grad": 0.05, "constraints_dDdt": 0.05, "constraints_color": 0.01,
+                              "range_distance": 1.0, "range_aux_grad": 1.0}
+        self.penalty_weight = {k: float(v) for k, v in dict(penalty_weight).items()}
+
+        # kernel-side state
+        self.engine = "auto"          # "auto" | "fp32" | "tc"
+        self._handle = None
+        self._handle_device = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ kernel plumbing --
+    def _ordered_layers(self) -> List[LinearGradLayer]:
+        return list(self.layers_ddf) + list(self.layers_col) + [self.layer_ddf_out, self.layer_aux_out, self.layer_col_out]
+
+    def _config_struct(self) -> L.FieldConfig:
+        c = L.FieldConfig()
+        c.embed_pos_rank, c.embed_dir_rank = self.embed_pos_rank, self.embed_dir_rank
+        c.ddf_layer_count, c.ddf_layer_width = self.ddf_layer_count, self.ddf_layer_width
+        c.col_layer_count, c.col_layer_width = self.col_layer_count, self.col_layer_width
+        c.activation_type = L.ACT_IDS[self.activation_type]
+        c.density_activation_type = L.ACT_IDS[self.density_activation_type]
+        c.d_near = self.d_near
+        if len(self.skips) > L.MAX_SKIPS:
+            raise NotImplementedError("neddf_b200: more than 8 skip connections")
+        c.n_skips = len(self.skips)
+        for i, s in enumerate(self.skips):
+            c.skips[i] = s
+        for i, k in enumerate(L.PENALTY_KEYS):  # absent key -> unweighted, neddf.py:296-299
+            c.penalty_weight[i] = self.penalty_weight.get(k, 1.0)
+        return c
+
+    def _state_struct(self) -> L.FieldState:
+        return L.FieldState(float(self.aux_grad_scale), float(self.distance_range_max), float(self.lowpass_alpha))
+
+    def _release(self) -> None:
+        if self._handle is not None:
+            try:
+                L.lib().neddf_field_destroy(self._handle)
+            except Exception:  # interpreter shutdown
+                pass
+            self._handle = None
+            self._packed_key = None
+
+    def __del__(self):
+        self._release()
+
+    def _field(self, device: torch.device):
+        """Handle with weights packed for the parameters' current values."""
+        lib = L.lib()
+        if device.type != "cuda":
+            raise RuntimeError("neddf_b200.NeDDF runs on CUDA devices only: move the module with .to('cuda') "
+                               "(the hot path has no CPU implementation)")
+        if self._handle is None or self._handle_device != device:
+            self._release()
+            h = C.c_void_p()
+            with torch.cuda.device(device):
+                cfg = self._config_struct()
+                L.check(lib.neddf_field_create(C.byref(cfg), C.byref(h)), "field_create")
+            self._handle, self._handle_device = h, device
+        layers = self._ordered_layers()
+        key = tuple((p.data_ptr(), p._version) for l in layers for p in (l.weight, l.bias)) + (
+            tuple(sorted(self.penalty_weight.items())),)
+        if key != self._packed_key:
+            n = len(layers)
+            ws = (C.c_void_p * n)(*[l.weight.data_ptr() for l in layers])
+            bs = (C.c_void_p * n)(*[l.bias.data_ptr() for l in layers])
+            for l in layers:
+                if l.weight.dtype != torch.float32 or not l.weight.is_contiguous() or l.weight.device != device:
+                    raise RuntimeError("neddf_b200: parameters must be contiguous fp32 tensors on the module's device")
+            with torch.cuda.device(device):
+                L.check(lib.neddf_field_set_weights(self._handle, ws, bs, n, L.stream_ptr(device)), "field_set_weights")
+            self._packed_key = key
+        return self._handle
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._packed_key = None  # .to()/.cuda() replaced the parameter storage
+        return r
+
+    def _check_no_grad(self) -> None:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "neddf_b200: the differentiable (training) path of the field kernel is not built yet; "
+                "call under torch.no_grad() / render_image. (Tracked in DESIGN.md, scope row a9.)")
+
+    # ------------------------------------------------------------------------- forward --
+    def forward(self, sampling: Sampling) -> Dict[str, Tensor]:
+        """NeDDF.forward (neddf.py:162-309): Sampling[B,S,3] -> distance, density, color,
+        fields_penalty, aux_grad."""
+        self._check_no_grad()
+        pos = sampling.sample_pos
+        B, S = pos.shape[0], pos.shape[1]
+        device = pos.device
+        # reshape, not view: accept the expanded tensors the reference's point sampler returns
+        p3 = L.require_cuda_f32(pos.reshape(-1, 3), "sample_pos")
+        d3 = L.require_cuda_f32(sampling.sample_dir.reshape(-1, 3), "sample_dir")
+        v3 = L.require_cuda_f32(sampling.diag_variance.reshape(-1, 3), "diag_variance")
+        n = B * S
+        out = {
+            "distance": torch.empty(B, S, device=device, dtype=torch.float32),
+            "density": torch.empty(B, S, device=device, dtype=torch.float32),
+            "color": torch.empty(B, S, 3, device=device, dtype=torch.float32),
+            "fields_penalty": torch.empty(B, S, device=device, dtype=torch.float32),
+            "aux_grad": torch.empty(B, S, device=device, dtype=torch.float32),
+        }
+        h = self._field(device)
+        st = self._state_struct()
+        with torch.cuda.device(device):
+            L.check(L.lib().neddf_field_forward(
+                h, C.byref(st), L.ptr(p3), L.ptr(d3), L.ptr(v3), n, L.ptr(out["distance"]), L.ptr(out["density"]),
+                L.ptr(out["color"]), L.ptr(out["fields_penalty"]), L.ptr(out["aux_grad"]), L.OUT_FULL,
+                L.ENGINE_IDS[self.engine], L.stream_ptr(device)), "field_forward")
+        return out
+
+    def forward_rays(self, ray_dir: Tensor, ray_orig: Tensor, dists: Tensor, sampling_type: str, ray_radius: float,
+                     need_penalty: bool = True, need_aux: bool = True) -> Dict[str, Tensor]:
+        """Same network with the sample geometry fused into the kernel prologue (no [N,3]
+        Sampling tensors in HBM).  Used by NeRFRender."""
+        self._check_no_grad()
+        B, S = dists.shape
+        device = dists.device
+        out = {
+            "density": torch.empty(B, S, device=device, dtype=torch.float32),
+            "color": torch.empty(B, S, 3, device=device, dtype=torch.float32),
+        }
+        if need_penalty:
+            out["fields_penalty"] = torch.empty(B, S, device=device, dtype=torch.float32)
+        if need_aux:
+            out["distance"] = torch.empty(B, S, device=device, dtype=torch.float32)
+            out["aux_grad"] = torch.empty(B, S, device=device, dtype=torch.float32)
+        h = self._field(device)
+        st = self._state_struct()
+        with torch.cuda.device(device):
+            L.check(L.lib().neddf_field_forward_rays(
+                h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, S, L.SAMPLING_IDS[sampling_type],
+                float(ray_radius), L.ptr(out.get("distance")), L.ptr(out["density"]), L.ptr(out["color"]),
+                L.ptr(out.get("fields_penalty")), L.ptr(out.get("aux_grad")),
+                L.OUT_FULL if need_penalty else L.OUT_EVAL, L.ENGINE_IDS[self.engine], L.stream_ptr(device)),
+                "field_forward_rays")
+        return out
+
+    def set_iter(self, iter: int) -> None:
+        """Warm-up schedule (neddf.py:311-326); -1 = evaluation."""
+        if iter == -1:
+            self.aux_grad_scale = 1.1
+            self.distance_range_max = 2.0
+            self.lowpass_alpha = float(self.embed_pos_rank)
+        else:
+            self.aux_grad_scale = min(1.1, max(0.01, 0.0001 * iter))
+            self.distance_range_max = min(2.0, 2.0 + 0.0001 * iter)
+            self.lowpass_alpha = self.lowpass_alpha_offset + 0.001 * iter

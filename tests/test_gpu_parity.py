@@ -1,0 +1,247 @@
+"""GPU parity tests: every kernel through the C ABI / host classes against the CPU oracle and the
+golden vectors of the real reference.  Tolerance: 1e-4 tensor-normalised (BASELINE.json
+north_star); searchsorted indices bit-exact given the same cdf."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import neddf_oracle as orc  # noqa: E402
+from tests.helpers import PARITY_TOL, Case, assert_parity, nerr  # noqa: E402
+
+CASES = ["bunny", "default", "point", "leaky"]
+ENGINES = ["fp32"]
+
+
+def _gpu():
+    import tests.gpu_util as G
+    return G
+
+
+def test_make_rays_and_samples():
+    G = _gpu()
+    import neddf_b200
+    c = Case("bunny")
+    render, cam = G.build_render(c), G.build_camera(c)
+    for dt in (torch.int64, torch.int32, torch.int16, torch.float32):
+        rays = render.create_rays(c.t("uv").to(dt).to(G.DEV), cam)
+        d_ref, o_ref = orc.make_rays(c.t("uv"), c.cam)
+        assert nerr(rays.ray_dir.cpu().numpy(), d_ref.numpy()) < 1e-6
+        assert nerr(rays.ray_orig.cpu().numpy(), o_ref.numpy()) == 0.0
+    dists = orc.coarse_dists(c.rc, c.t("u_coarse"))
+    for kind in ("cone", "point"):
+        s = rays.get_sampling_cones(dists.to(G.DEV), neddf_b200.CONE_RAY_RADIUS) if kind == "cone" \
+            else rays.get_sampling_points(dists.to(G.DEV))
+        rc = orc.RenderConfig(sampling_type=kind)
+        pos, d, var = orc.make_samples(rc, d_ref, o_ref, dists)
+        assert nerr(s.sample_pos.cpu().numpy(), pos.numpy()) < 1e-6
+        assert nerr(s.sample_dir.cpu().numpy(), d.numpy()) < 1e-6
+        if kind == "cone":
+            assert nerr(s.diag_variance.cpu().numpy(), var.numpy()) < 1e-5
+        else:
+            assert float(s.diag_variance.abs().max()) == 0.0
+
+
+def test_coarse_dists_exact():
+    G = _gpu()
+    from neddf_b200 import _lib as L
+    for (near, far, S) in ((2.0, 6.0, 64), (1.5, 5.5, 32), (0.1, 9.7, 100)):
+        u = torch.rand(37, S + 1, generator=torch.Generator().manual_seed(5))
+        ref = orc.coarse_dists(orc.RenderConfig(sample_coarse=S, dist_near=near, dist_far=far), u)
+        ud = u.to(G.DEV)
+        out = torch.empty_like(ud)
+        L.check(L.lib().neddf_coarse_dists(L.ptr(ud), 37, S + 1, near, far, L.ptr(out), L.stream_ptr(G.DEV)))
+        # same formula as torch.linspace + fp32 multiply-add; FMA contraction may move one ulp
+        assert nerr(out.cpu().numpy(), ref.numpy()) < 2e-7
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_composite_matches_reference(name):
+    G = _gpu()
+    c = Case(name)
+    render = G.build_render(c)
+    d_ref, o_ref = orc.make_rays(c.t("uv"), c.cam)
+    for tag, dists in (("coarse", orc.coarse_dists(c.rc, c.t("u_coarse"))), ("fine", c.t("dists_fine"))):
+        dens, col, pen = c.t(f"field_{tag}_density"), c.t(f"field_{tag}_color"), c.t(f"field_{tag}_fields_penalty")
+        got = render.integrate_volume_render(dists.to(G.DEV), dens.to(G.DEV), col.to(G.DEV), pen.to(G.DEV))
+        ref = orc.composite(dists, dens, col, c.rc.max_dist)
+        ref["fields_penalty"] = orc.integrate_penalty(dists, pen)
+        for k, v in ref.items():
+            assert nerr(got[k].cpu().numpy(), v.numpy()) < 2e-6, (tag, k)
+        if tag == "fine":  # and against the real reference's composited outputs
+            for k in ("weight", "depth", "color", "transmittance", "fields_penalty"):
+                assert nerr(got[k].cpu().numpy(), c.z["out_" + k]) < 1e-5, k
+    render.check_status()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sample_pdf_indices_bit_exact(name):
+    G = _gpu()
+    from neddf_b200 import _lib as L
+    c = Case(name)
+    render = G.build_render(c)
+    dists = orc.coarse_dists(c.rc, c.t("u_coarse"))
+    w = torch.from_numpy(c.z["out_weight_coarse"]).clone()
+    u = c.t("u_fine")
+    cdf = orc.pdf_cdf(w)
+    new_ref, ids_ref = orc.invert_cdf(dists, cdf, u)
+    B, E = dists.shape
+    F = u.shape[1]
+    ids = torch.empty(B, F, dtype=torch.int64, device=G.DEV)
+    smp = torch.empty(B, F, dtype=torch.float32, device=G.DEV)
+    L.check(L.lib().neddf_invert_cdf(L.ptr(dists.to(G.DEV)), L.ptr(cdf.to(G.DEV)), L.ptr(u.to(G.DEV)), B, E, F,
+                                     L.ptr(smp), L.ptr(ids), L.stream_ptr(G.DEV)))
+    assert torch.equal(ids.cpu(), ids_ref)  # bit-exact sample indices given the same cdf
+    assert nerr(smp.cpu().numpy(), new_ref.numpy()) < 1e-6
+    # full kernel: own cdf (fp64 scan), merge + sort
+    wd = w.to(G.DEV).contiguous()
+    out, ids2 = render.sample_pdf(dists.to(G.DEV), wd, F, uniform_rands=u.to(G.DEV), return_ids=True)
+    ref = orc.sample_pdf(dists, w, u)
+    assert nerr(out.cpu().numpy(), ref.numpy()) < 1e-6
+    assert nerr(out.cpu().numpy(), c.z["dists_fine"]) < 1e-6
+    mism = float((ids2.cpu() != ids_ref).float().mean())
+    assert mism < 1e-3, mism  # cdf bits may differ in the last ulp from torch's summation order
+    o = out.cpu()
+    assert bool((o[:, 1:] >= o[:, :-1]).all())
+
+
+def test_sample_pdf_sanitises_and_nan_fallback():
+    G = _gpu()
+    c = Case("bunny")
+    render = G.build_render(c)
+    dists = orc.coarse_dists(c.rc, c.t("u_coarse"))[:4]
+    w = torch.rand(4, 64, generator=torch.Generator().manual_seed(1)) - 0.3
+    w[1, 5] = float("nan")
+    u = c.t("u_fine")[:4]
+    wd = w.clone().to(G.DEV)
+    out = render.sample_pdf(dists.to(G.DEV), wd, u.shape[1], uniform_rands=u.to(G.DEV))
+    ref = orc.sample_pdf(dists, w.clone(), u)
+    assert nerr(out.cpu().numpy(), ref.numpy()) < 1e-6
+    assert torch.equal(wd.cpu(), orc.sanitise_weights(w))  # in-place side effect, base_neural_render.py:52-55
+    # NaN distances -> batch-wide linspace fallback (base_neural_render.py:105-114)
+    dn = dists.clone()
+    dn[2, 10] = float("nan")
+    out = render.sample_pdf(dn.to(G.DEV), w.clone().to(G.DEV), u.shape[1], uniform_rands=u.to(G.DEV))
+    ref = torch.linspace(float(dn[0, 0]), float(dn[0, -1]), out.shape[1]).reshape(1, -1).expand(4, -1)
+    assert nerr(out.cpu().numpy(), ref.numpy()) < 1e-6
+    render._status_buf.zero_()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", CASES)
+def test_field_forward_matches_reference(name, engine):
+    """NeDDF.forward on the reference's own fine samples (Sampling tensors) vs the reference."""
+    G = _gpu()
+    import neddf_b200
+    c = Case(name)
+    render = G.build_render(c, engine)
+    d_ref, o_ref = orc.make_rays(c.t("uv"), c.cam)
+    pos, dd, var = orc.make_samples(c.rc, d_ref, o_ref, c.t("dists_fine"))
+    with torch.no_grad():
+        out = render.network_fine(neddf_b200.Sampling(pos.to(G.DEV), dd.contiguous().to(G.DEV), var.to(G.DEV)))
+    for k in ("distance", "density", "color", "fields_penalty", "aux_grad"):
+        assert_parity(out[k].cpu().numpy(), c.z["field_fine_" + k], PARITY_TOL, c.kinked, k)
+    # fused-geometry entry point gives the same numbers
+    with torch.no_grad():
+        out2 = render.network_fine.forward_rays(d_ref.to(G.DEV), o_ref.to(G.DEV).contiguous(), c.t("dists_fine").to(G.DEV),
+                                                c.rc.sampling_type, render._ray_radius, True, True)
+    for k in ("distance", "density", "color", "fields_penalty", "aux_grad"):
+        assert_parity(out2[k].cpu().numpy(), c.z["field_fine_" + k], PARITY_TOL, c.kinked, k)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_field_forward_ragged_and_empty(engine):
+    G = _gpu()
+    import neddf_b200
+    c = Case("default")
+    render = G.build_render(c, engine)
+    g = torch.Generator().manual_seed(3)
+    for n in (0, 1, 15, 17, 16 * 148 + 5):
+        pos = (torch.rand(1, n, 3, generator=g) - 0.5) * 2.0
+        dd = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1)
+        var = torch.rand(1, n, 3, generator=g) * 1e-3
+        with torch.no_grad():
+            out = render.network_fine(neddf_b200.Sampling(pos.to(G.DEV), dd.to(G.DEV), var.to(G.DEV)))
+        assert out["density"].shape == (1, n)
+        if n == 0:
+            continue
+        ref = orc.field_forward(c.p_fine, c.fc, c.st, pos, dd, var)
+        for k, v in ref.items():
+            assert nerr(out[k].cpu().numpy(), v.numpy()) < PARITY_TOL, (n, k)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", CASES)
+def test_render_rays_matches_reference(name, engine):
+    G = _gpu()
+    c = Case(name)
+    render, cam = G.build_render(c, engine), G.build_camera(c)
+    with torch.no_grad():
+        out = render.render_rays(c.t("uv").to(G.DEV), cam, uniforms=(c.t("u_coarse").to(G.DEV), c.t("u_fine").to(G.DEV)))
+    ref = c.outputs()
+    assert set(out.keys()) == set(ref.keys())
+    for k, v in ref.items():
+        assert tuple(out[k].shape) == v.shape, k
+        assert_parity(out[k].cpu().numpy(), v, PARITY_TOL, c.kinked, k)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_render_image_matches_reference_image(engine):
+    """bunny_smoke test frame 0 at downsampling 10 with the recorded uniforms: PSNR(new, ref)
+    and PSNR vs ground truth like base_trainer.py:146-174."""
+    import os
+    G = _gpu()
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "case_image.npz"))
+    c = Case("bunny")
+    render, cam = G.build_render(c, engine), G.build_camera(c)
+    w, h, ds = int(z["width"]), int(z["height"]), int(z["downsampling"])
+    n_pix = (w // ds) * (h // ds)
+    g = torch.Generator().manual_seed(int(z["rand_seed"]))
+    u_c = torch.rand(n_pix, 65, generator=g)
+    u_f = torch.rand(n_pix, 129, generator=g)
+    img = render.render_image(w, h, cam, ["color", "depth", "transmittance"], ds, 500, uniforms=(u_c, u_f))
+    assert img["color"].shape == (h // ds, w // ds, 3) and img["depth"].shape == (h // ds, w // ds, 1)
+    for k in ("color", "depth", "transmittance"):
+        assert nerr(img[k].cpu().numpy(), z[k]) < PARITY_TOL, k
+    mse = float(((img["color"].cpu().numpy().astype(np.float64) - z["color"]) ** 2).mean())
+    psnr_new_ref = 10 * np.log10(1.0 / max(mse, 1e-30))
+    assert psnr_new_ref > 80.0, psnr_new_ref
+    rgb = np.clip(img["color"].cpu().numpy() * 255, 0, 255).astype(np.uint8)
+    mse_gt = np.mean((rgb.astype(np.float64) - z["gt_bgr_u8"].astype(np.float64)) ** 2)
+    assert 10 * np.log10(255.0 ** 2 / mse_gt) > 42.5  # reference: 43.09 dB
+    assert render.network_fine.training and render.network_coarse.training  # nerf_render.py:247-248
+
+
+def test_device_rng_default_and_determinism():
+    G = _gpu()
+    c = Case("bunny")
+    render, cam = G.build_render(c), G.build_camera(c)
+    uv = c.t("uv").to(G.DEV)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        a = render.render_rays(uv, cam)
+        torch.manual_seed(0)
+        b = render.render_rays(uv, cam)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert bool(torch.isfinite(a["color"]).all())
+
+
+def test_errors_are_loud():
+    G = _gpu()
+    import neddf_b200
+    c = Case("bunny")
+    render, cam = G.build_render(c), G.build_camera(c)
+    with pytest.raises(RuntimeError):
+        render.render_rays(c.t("uv"), cam)  # CPU uv
+    with pytest.raises(NotImplementedError):
+        render.render_rays(c.t("uv").to(G.DEV), cam)  # grad enabled: training path not built yet
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            render.render_rays(c.t("uv").to(G.DEV), cam, uniforms=(torch.rand(3, 65), torch.rand(3, 129)))
+    with pytest.raises(NotImplementedError):
+        neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeRF"})

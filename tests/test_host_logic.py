@@ -1,0 +1,61 @@
+"""CPU: host-side mirror of the reference interface (no kernels run)."""
+import numpy as np
+import pytest
+import torch
+
+import neddf_b200
+from oracle import neddf_oracle as orc
+from tests.helpers import Case
+
+
+def test_state_dict_surface_matches_reference_checkpoint():
+    c = Case("bunny")
+    r = neddf_b200.NeRFRender(network_config=c.net_cfg, **{k: v for k, v in c.render_cfg.items() if k != "_target_"})
+    sd = r.state_dict()
+    assert len(sd) == 52  # network_fine.* and network_coarse.* alias the same tensors
+    assert r.network_coarse is r.network_fine
+    res = r.load_state_dict(c.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys
+    assert len(r.get_parameters_list()) == 26
+    r2 = neddf_b200.NeRFRender(network_config=c.net_cfg, use_coarse_network=True)
+    assert r2.network_coarse is not r2.network_fine and len(r2.get_parameters_list()) == 52
+
+
+def test_set_iter_schedule_matches_reference():
+    net = neddf_b200.NeDDF(lowpass_alpha_offset=4.0)
+    cfg = orc.FieldConfig(lowpass_alpha_offset=4.0)
+    for it in (-1, 0, 50, 2500, 20000):
+        net.set_iter(it)
+        st = orc.FieldState.at_iter(cfg, it)
+        assert (net.aux_grad_scale, net.distance_range_max, net.lowpass_alpha) == \
+            (st.aux_grad_scale, st.distance_range_max, st.lowpass_alpha)
+    r = neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeDDF"})
+    r.set_iter(7)
+    r.next_iter()
+    assert r.iteration == 8 and r.network_fine.aux_grad_scale == pytest.approx(0.01)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    net = neddf_b200.NeDDF()
+    s = neddf_b200.Sampling(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        net(s)
+
+
+def test_unknown_network_target_is_rejected():
+    with pytest.raises(NotImplementedError):
+        neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeuS"})
+    with pytest.raises(KeyError):
+        neddf_b200.NeDDF(activation_type="gelu")
+
+
+def test_camera_standin_matches_reference_pose():
+    c = Case("bunny")
+    cam = neddf_b200.Camera.from_matrix(neddf_b200.PinholeCalib(c.z["cam_calib"]), c.z["cam_R"], c.z["cam_T"])
+    assert np.allclose(cam.R.numpy(), c.z["cam_R"]) and np.allclose(cam.T.numpy(), c.z["cam_T"])
+    # rotvec path: Rodrigues of a known rotation
+    from scipy.spatial.transform import Rotation
+    rv = np.array([0.3, -1.1, 0.7])
+    cam2 = neddf_b200.Camera(neddf_b200.PinholeCalib([100, 100, 50, 50]), np.concatenate([rv, [1, 2, 3]]))
+    assert np.allclose(cam2.R.numpy(), Rotation.from_rotvec(rv).as_matrix(), atol=1e-6)
+    assert np.allclose(cam2.T.numpy(), [1, 2, 3])
