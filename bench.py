@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the NeDDF render hot path (BASELINE.json metric: ray-samples/s, 800x800x192).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+A "step" is one 800x800 frame (640,000 rays, 64 coarse + 128 fine samples/ray = 192 nominal
+ray-samples = 259 MLP evaluations per ray), synthetic camera on the radius-4.03 sphere, seeded
+random-init NeDDF weights of the reference architecture (8x256 distance trunk with skip, 4x256
+colour trunk, tanhExp, cone sampling).  With N GPUs a step is N frames, every frame ray-sharded
+over the N ranks with ONE all-gather of image tiles per frame (weak scaling: 640k rays per rank
+per step).
+
+Prints ONE JSON line (rank 0).  `value` = nominal ray-samples/s with the frame's uniforms
+resident in HBM; `e2e` = the same through NeRFRender.render_image with HOST buffers (uniforms
+copied from pinned memory, image copied back) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 800
+S_COARSE, S_FINE = 64, 128
+NOMINAL_PER_RAY = S_COARSE + S_FINE            # 192
+EVALS_PER_RAY = (S_COARSE + 1) + (S_COARSE + 1 + S_FINE + 1)  # 65 + 194 = 259
+# algorithmic FLOP per MLP evaluation: 4 rows through the distance trunk + heads,
+# 1 row through the colour trunk (eval outputs) / 4 rows everywhere (fields_penalty produced)
+F_EVAL, F_FULL = 3_834_880, 5_152_768
+
+NET_CFG = dict(_target_="neddf.network.NeDDF", embed_pos_rank=10, embed_dir_rank=4, ddf_layer_count=8,
+               ddf_layer_width=256, col_layer_count=4, col_layer_width=256, d_near=0.001,
+               activation_type="tanhExp", density_activation_type="ReLU", lowpass_alpha_offset=10,
+               penalty_weight=dict(constraints_aux_grad=0.05, constraints_dDdt=1.0, constraints_color=0.0001,
+                                   range_distance=1.0, range_aux_grad=1.0, range_color=0.1), skips=[4])
+RENDER_CFG = dict(sample_coarse=S_COARSE, sample_fine=S_FINE, dist_near=2.0, dist_far=6.0, max_dist=6.0,
+                  use_coarse_network=False, sampling_type="cone")
+WEIGHT_SEED = 3408
+
+
+def synthetic_pose(seed: int):
+    """Camera on the radius-4.0311 sphere looking at the origin."""
+    import numpy as np
+    g = np.random.default_rng(seed)
+    v = g.normal(size=3)
+    v /= np.linalg.norm(v)
+    back = v
+    right = np.cross([0.0, 0.0, 1.0], back)
+    right /= np.linalg.norm(right)
+    up = np.cross(back, right)
+    R = np.stack([right, up, back], 1).astype(np.float32)
+    T = (4.0311 * v).astype(np.float32)
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    return R, T, np.array([focal, focal, 0.5 * W, 0.5 * H], dtype=np.float32)
+
+
+def seeded_state_dict():
+    """Xavier-normal weights [in,out] like LinearGradLayer's init, from a fixed seed (same
+    generator the oracle uses, so both arms see identical weights)."""
+    from oracle import neddf_oracle as orc
+    fc = orc.FieldConfig.from_dict(NET_CFG)
+    p = orc.init_params(fc, WEIGHT_SEED, bias_std=0.05)
+    sd = {"network_fine." + k: v for k, v in p.items()}
+    sd.update({"network_coarse." + k: v for k, v in p.items()})
+    return sd, p, fc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_rate(n_rays: int, threads: int):
+    """The reference algorithm (oracle port, torch CPU fp32, same op structure as the reference)
+    on a bounded sample of the workload: `n_rays` rays of the same frame."""
+    from oracle import neddf_oracle as orc
+    torch.set_num_threads(threads)
+    sd, p, fc = seeded_state_dict()
+    rc = orc.RenderConfig(**RENDER_CFG)
+    st = orc.FieldState.at_iter(fc, -1)
+    R, T, calib = synthetic_pose(0)
+    cam = orc.CameraPose(torch.from_numpy(R), torch.from_numpy(T), *[float(c) for c in calib])
+    uv = orc.image_uv(W, H)
+    g = torch.Generator().manual_seed(1)
+    sel = torch.randint(0, uv.shape[0], (n_rays,), generator=g)
+    u_c = torch.rand(n_rays, S_COARSE + 1, generator=g)
+    u_f = torch.rand(n_rays, S_FINE + 1, generator=g)
+    with torch.no_grad():
+        orc.render_rays(p, p, fc, st, rc, uv[sel[:32]], cam, u_c[:32], u_f[:32])  # warm-up
+        t0 = time.perf_counter()
+        orc.render_rays(p, p, fc, st, rc, uv[sel], cam, u_c, u_f)
+        dt = time.perf_counter() - t0
+    return n_rays * NOMINAL_PER_RAY / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on
+    the GPU box) timed on host cores, same workload/metric, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_rays = args.cpu_rays
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, dt = cpu_port_rate(n_rays, threads)
+        if i >= args.warmup:
+            rates.append((r, dt))
+    value = sum(r for r, _ in rates) / len(rates)
+    ms = 1e3 * sum(dt for _, dt in rates) / len(rates)
+    line = {
+        "impl": "reference", "metric": "ray-samples/s (800x800x192)", "value": value, "unit": "ray-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_rays} random rays of the 800x800 frame per step ({n_rays * EVALS_PER_RAY} MLP evaluations)"},
+        "e2e": {"value": value, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, engine):
+    return {"workload": "lego-shaped synthetic 800x800 frame, 64 coarse + 128 fine samples/ray, cone sampling, "
+                        "NeDDF 8x256 + 4x256 tanhExp, seeded random-init weights",
+            "rays_per_frame": W * H, "frames_per_step": n_gpus, "nominal_samples_per_ray": NOMINAL_PER_RAY,
+            "mlp_evaluations_per_ray": EVALS_PER_RAY, "engine": engine,
+            "parallelism": f"ray-sharded x{n_gpus}, one all-gather of image tiles per frame" if n_gpus > 1 else "single GPU",
+            "l2": "per-frame uniforms are 497 MB (> 126 MB L2) and every step reads fresh ones; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--cpu-rays", type=int, default=384, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rules: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    import neddf_b200
+    from neddf_b200 import _lib as L
+    from neddf_b200.dist import render_image_sharded, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the render hot path has no CPU implementation "
+                         "(use --impl reference for the host-core baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    sd, _, _ = seeded_state_dict()
+    render = neddf_b200.NeRFRender(network_config=NET_CFG, **RENDER_CFG)
+    render.load_state_dict(sd)
+    render.to(dev)
+    render.set_iter(-1)
+    render.set_engine(args.engine)
+    render.check_nan = False  # no host sync inside the timed region; checked once after it
+    n_pix = W * H
+    first, count = shard_range(n_pix, world, rank)
+    n_frames = n_gpus  # frames per step
+    cams = []
+    for f in range(n_frames):
+        R, T, calib = synthetic_pose(f)
+        cam = neddf_b200.Camera.from_matrix(neddf_b200.PinholeCalib(calib), R, T).to(dev)
+        cam.update_transform()
+        cams.append(cam)
+
+    # host-side inputs of one step (pinned): the uniforms of this rank's slice of every frame
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_u = [(torch.rand(count, S_COARSE + 1, generator=g).pin_memory(),
+               torch.rand(count, S_FINE + 1, generator=g).pin_memory()) for _ in range(n_frames)]
+    dev_u = [(a.to(dev), b.to(dev)) for a, b in host_u]
+    targets = ["color", "depth"]
+
+    def step_device():
+        outs = []
+        for f in range(n_frames):
+            flat = render.render_pixels(W, H, cams[f], targets, 1, first, count, dev_u[f])
+            if world > 1:
+                from neddf_b200.dist import gather_tiles
+                packed = torch.cat([flat["color"], flat["depth"]], 1)
+                outs.append(gather_tiles(packed, n_pix))
+            else:
+                outs.append(flat)
+        return outs
+
+    def step_e2e():
+        """Public API with host buffers: H2D of the uniforms, render_image (sharded when N>1),
+        D2H of colour + depth."""
+        res = []
+        for f in range(n_frames):
+            u = (host_u[f][0].to(dev, non_blocking=True), host_u[f][1].to(dev, non_blocking=True))
+            if world > 1:
+                flat = render.render_pixels(W, H, cams[f], targets, 1, first, count, u)
+                from neddf_b200.dist import gather_tiles
+                img = gather_tiles(torch.cat([flat["color"], flat["depth"]], 1), n_pix)
+                if rank == 0:
+                    res.append(img.to("cpu", non_blocking=False))
+            else:
+                img = render.render_image(W, H, cams[f], targets, 1, 1024, uniforms=u)
+                res.append((img["color"].cpu(), img["depth"].cpu()))
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            render.network_fine._profile_events = []
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        evs = None
+        if profile:
+            evs = render.network_fine._profile_events
+            render.network_fine._profile_events = None
+        return float(t.item()), evs
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lib().neddf_launch_count()
+    ms_total, evs = timed(step_device, args.steps, profile=True)
+    launches = L.lib().neddf_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    render.check_status()
+    ms_step = ms_total / args.steps
+    rays_per_step = n_pix * n_frames
+    value = rays_per_step * NOMINAL_PER_RAY / (ms_step * 1e-3)
+
+    # dominant kernel: the field megakernel.  Launch durations from CUDA events recorded around
+    # every launch on the launching stream, inside the timed region above.
+    evals, kms = 0, 0.0
+    for (e0, e1, n_eval) in evs:
+        kms += e0.elapsed_time(e1)
+        evals += n_eval
+    flop = F_EVAL
+    achieved_tflops = evals * flop / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "field_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+
+    # end to end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, max(1, args.steps))
+    ms_e2e /= max(1, args.steps)
+    e2e_value = rays_per_step * NOMINAL_PER_RAY / (ms_e2e * 1e-3)
+    h2d = n_frames * count * (S_COARSE + 1 + S_FINE + 1) * 4 + n_frames * 16 * 4
+    d2h = n_frames * n_pix * 4 * 4 if rank == 0 else 0
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_port_rate(args.cpu_rays, threads)
+        cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_rays} random rays of the same 800x800 frame ({args.cpu_rays * EVALS_PER_RAY} MLP evaluations, {dt:.1f} s)"}
+
+    if rank == 0:
+        engine = render.network_fine.resolved_engine(dev)
+        line = {
+            "metric": "ray-samples/s (800x800x192)", "value": value, "unit": "ray-samples/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if engine == "fp32" else "f16x3-split operands, f32 accumulate (f32 on the fp32 engine)",
+            "data": "synthetic", "config": workload_config(n_gpus, engine),
+            "mlp_evaluations_per_s": rays_per_step * EVALS_PER_RAY / (ms_step * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / peak if peak else None, "traffic": traffic,
+                         "kernel": "field megakernel (NeDDF.forward fused)", "peak_source": peak_src,
+                         "flop_per_evaluation": flop, "launches_timed": len(evs),
+                         "kernel_share_of_step": kms / ms_total if ms_total else None},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,10 @@ int32_t neddf_field_layer_shapes(const neddf_field_config_t* cfg, int32_t* shape
 int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_field_t** out);
 int32_t neddf_field_destroy(neddf_field_t* f);
 
+/* Which engine a NEDDF_ENGINE_* request resolves to for this field (AUTO -> TC when the
+ * tensor-core megakernel covers the configuration, else FP32). */
+int32_t neddf_field_resolve_engine(const neddf_field_t* f, int32_t engine);
+
 /* Re-pack the module's parameters into kernel layout.  d_weights[i] is the i-th layer's
  * weight, fp32 [in,out] row-major exactly as LinearGradLayer stores it
  * (nn_module/with_grad/linear.py:111-116); d_biases[i] its bias [out].  Must be called

@@ -207,6 +207,14 @@ extern "C" int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_fie
   return NEDDF_OK;
 }
 
+extern "C" int32_t neddf_field_resolve_engine(const neddf_field_t* f, int32_t engine) {
+  if (!f) return fail(NEDDF_E_INVALID, "neddf_field_resolve_engine: field is NULL");
+  if (engine == NEDDF_ENGINE_AUTO) return tc_supported(f) ? NEDDF_ENGINE_TC : NEDDF_ENGINE_FP32;
+  if (engine == NEDDF_ENGINE_TC && !tc_supported(f)) return fail(NEDDF_E_UNSUPPORTED, "tensor-core engine does not cover this configuration");
+  if (engine != NEDDF_ENGINE_FP32 && engine != NEDDF_ENGINE_TC) return fail(NEDDF_E_INVALID, "unknown engine id");
+  return engine;
+}
+
 extern "C" int32_t neddf_field_destroy(neddf_field_t* f) {
   if (!f) return NEDDF_OK;
   tc_destroy(f);

@@ -12,18 +12,20 @@ struct CamParams {
 
 // neddf/camera/camera.py:166-187 + pinhole_calib.py:64-73
 __device__ __forceinline__ void unproject(const CamParams& c, float u, float v, float dir[3]) {
-  float uc = 0.5f + u, vc = 0.5f + v;  // get_center_of_pixels, scale = 1
-  float x = (1.0f / c.fx) * (uc - c.cx);
-  float y = (1.0f / c.fy) * (vc - c.cy);
+  // separate roundings like the reference's tensor ops (see common.cuh NM/NA/NS)
+  float uc = NA(0.5f, u), vc = NA(0.5f, v);  // get_center_of_pixels, scale = 1
+  float x = NM(__frcp_rn(c.fx), NS(uc, c.cx));
+  float y = NM(__frcp_rn(c.fy), NS(vc, c.cy));
   // RDF -> RUB flip then L2 normalise (F.normalize: v / max(|v|, 1e-12))
   float lx = x, ly = -y, lz = -1.0f;
-  float nrm = sqrtf(lx * lx + ly * ly + lz * lz);
+  float nrm = __fsqrt_rn(NA(NA(NM(lx, lx), NM(ly, ly)), NM(lz, lz)));
   float inv = fmaxf(nrm, 1e-12f);
-  lx = lx / inv;
-  ly = ly / inv;
-  lz = lz / inv;
+  lx = __fdiv_rn(lx, inv);
+  ly = __fdiv_rn(ly, inv);
+  lz = __fdiv_rn(lz, inv);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) dir[i] = c.R[i * 3 + 0] * lx + c.R[i * 3 + 1] * ly + c.R[i * 3 + 2] * lz;
+  for (int i = 0; i < 3; ++i)
+    dir[i] = NA(NA(NM(c.R[i * 3 + 0], lx), NM(c.R[i * 3 + 1], ly)), NM(c.R[i * 3 + 2], lz));
 }
 
 template <typename T>
@@ -61,7 +63,7 @@ __global__ void coarse_dists_kernel(const float* __restrict__ u, int64_t total, 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int j = (int)(i % n_edges);
-  dists[i] = linspace_at(near_, far_, n_edges, j) + u[i] * jitter;
+  dists[i] = NA(linspace_at(near_, far_, n_edges, j), NM(u[i], jitter));
 }
 
 __global__ void make_samples_kernel(const float* __restrict__ ray_dir, const float* __restrict__ ray_orig,

@@ -32,10 +32,10 @@ __device__ __forceinline__ float invert_one(const float* __restrict__ cdf, const
   int above = min(n_edges - 1, id);
   float c0 = cdf[below], c1 = cdf[above];
   float d0 = dists[below], d1 = dists[above];
-  float denom = c1 - c0;
+  float denom = NS(c1, c0);
   if (denom < 1e-5f) denom = 1.0f;
-  float t = (u - c0) / denom;
-  return d0 + t * (d1 - d0);
+  float t = __fdiv_rn(NS(u, c0), denom);
+  return NA(d0, NM(t, NS(d1, d0)));
 }
 
 // smem per warp: cdf[n_edges] | dists[n_edges] | merged[p2]

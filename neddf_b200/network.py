@@ -129,6 +129,13 @@ class NeDDF(BaseNeuralField):
         self._handle = None
         self._handle_device = None
         self._packed_key = None
+        self._profile_events = None   # bench.py: list receiving (start, end, n_evaluations) CUDA events
+
+    def resolved_engine(self, device=None) -> str:
+        """Engine that will actually run for ``self.engine`` ("fp32" or "tc")."""
+        h = self._field(torch.device(device) if device is not None else self.device)
+        rc = L.check(L.lib().neddf_field_resolve_engine(h, L.ENGINE_IDS[self.engine]), "resolve_engine")
+        return {1: "fp32", 2: "tc"}[rc]
 
     # ------------------------------------------------------------------ kernel plumbing --
     def _ordered_layers(self) -> List[LinearGradLayer]:
@@ -164,7 +171,10 @@ class NeDDF(BaseNeuralField):
             self._packed_key = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:  # interpreter shutdown: torch internals may already be gone
+            pass
 
     def _field(self, device: torch.device):
         """Handle with weights packed for the parameters' current values."""
@@ -252,6 +262,10 @@ class NeDDF(BaseNeuralField):
             out["aux_grad"] = torch.empty(B, S, device=device, dtype=torch.float32)
         h = self._field(device)
         st = self._state_struct()
+        prof = self._profile_events
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(device))
         with torch.cuda.device(device):
             L.check(L.lib().neddf_field_forward_rays(
                 h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, S, L.SAMPLING_IDS[sampling_type],
@@ -259,6 +273,9 @@ class NeDDF(BaseNeuralField):
                 L.ptr(out.get("fields_penalty")), L.ptr(out.get("aux_grad")),
                 L.OUT_FULL if need_penalty else L.OUT_EVAL, L.ENGINE_IDS[self.engine], L.stream_ptr(device)),
                 "field_forward_rays")
+        if prof is not None:
+            e1.record(torch.cuda.current_stream(device))
+            prof.append((e0, e1, B * S))
         return out
 
     def set_iter(self, iter: int) -> None:
