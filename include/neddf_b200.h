@@ -105,6 +105,11 @@ int32_t neddf_field_destroy(neddf_field_t* f);
  * tensor-core megakernel covers the configuration, else FP32). */
 int32_t neddf_field_resolve_engine(const neddf_field_t* f, int32_t engine);
 
+/* Read and clear the field's device status word (synchronises `stream`): bit 2 (value 4) = the
+ * tensor-core engine met an activation outside fp16 range (|x| > 65504); results of that call are
+ * invalid and the caller should use NEDDF_ENGINE_FP32 for this network. */
+int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* stream);
+
 /* Re-pack the module's parameters into kernel layout.  d_weights[i] is the i-th layer's
  * weight, fp32 [in,out] row-major exactly as LinearGradLayer stores it
  * (nn_module/with_grad/linear.py:111-116); d_biases[i] its bias [out].  Must be called

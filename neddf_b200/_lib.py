@@ -50,6 +50,7 @@ _SIGNATURES = {
     "neddf_field_create": (_I32, [C.POINTER(FieldConfig), C.POINTER(_P)]),
     "neddf_field_destroy": (_I32, [_P]),
     "neddf_field_resolve_engine": (_I32, [_P, _I32]),
+    "neddf_field_status": (_I32, [_P, C.POINTER(C.c_int32), _P]),
     "neddf_field_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P]),
     "neddf_make_rays": (_I32, [_P, _I32, _I64, _FP, _FP, _FP, _P, _P, _P]),
     "neddf_make_image_rays": (_I32, [_I32, _I32, _I32, _I64, _I64, _FP, _FP, _FP, _P, _P, _P]),

@@ -30,18 +30,25 @@ struct PackArgs {
   int n_hidden;
 };
 
-// Hidden layers: dst[(row_off + r)][(c % 16) * 16 + c / 16] = W[r][c] (zero rows up to k_pad):
-// thread (s, cg) of the fp32 kernel then finds its 16 channels {cg + 16 i} contiguous.
+// Hidden layers: channel c = cg + 16 i (cg = c % 16, i = c / 16) is stored at column
+// (i / 4) * 64 + cg * 4 + (i % 4), rows zero-padded up to k_pad.  Thread (s, cg) of the fp32
+// kernel owns channels {cg + 16 i}; its q-th float4 (i = 4q..4q+3) sits at q*64 + cg*4, so the
+// 16 lanes of a half-warp read 256 contiguous bytes per LDS.128 (no bank conflicts).
+__device__ __forceinline__ int simt_col(int c) {
+  int cg = c % 16, i = c / 16;
+  return (i / 4) * 64 + cg * 4 + (i % 4);
+}
+
 __global__ void pack_hidden_kernel(PackArgs a, float* __restrict__ w_dst, float* __restrict__ b_dst) {
   const int l = blockIdx.y;
   const int total = a.k_pad[l] * kWidth;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int r = idx / kWidth, c = idx % kWidth;
     float v = (r < a.k_in[l]) ? a.w[l][(size_t)r * kWidth + c] : 0.f;
-    w_dst[(size_t)(a.row_off[l] + r) * kWidth + (c % 16) * 16 + c / 16] = v;
+    w_dst[(size_t)(a.row_off[l] + r) * kWidth + simt_col(c)] = v;
   }
   if (blockIdx.x == 0)
-    for (int c = threadIdx.x; c < kWidth; c += blockDim.x) b_dst[l * kWidth + (c % 16) * 16 + c / 16] = a.b[l][c];
+    for (int c = threadIdx.x; c < kWidth; c += blockDim.x) b_dst[l * kWidth + simt_col(c)] = a.b[l][c];
 }
 
 __global__ void pack_heads_kernel(PackArgs a, float* __restrict__ da, float* __restrict__ col,
@@ -213,6 +220,14 @@ extern "C" int32_t neddf_field_resolve_engine(const neddf_field_t* f, int32_t en
   if (engine == NEDDF_ENGINE_TC && !tc_supported(f)) return fail(NEDDF_E_UNSUPPORTED, "tensor-core engine does not cover this configuration");
   if (engine != NEDDF_ENGINE_FP32 && engine != NEDDF_ENGINE_TC) return fail(NEDDF_E_INVALID, "unknown engine id");
   return engine;
+}
+
+extern "C" int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* stream) {
+  if (!f || !h_status_out) return fail(NEDDF_E_INVALID, "neddf_field_status: NULL argument");
+  int v = 0;
+  int32_t rc = tc_read_status(f, &v, (cudaStream_t)stream);
+  *h_status_out = v;
+  return rc;
 }
 
 extern "C" int32_t neddf_field_destroy(neddf_field_t* f) {

@@ -20,8 +20,8 @@
 //     [off_es, off_es+n_e0) scaled position embedding E_s (layer-0 input and skip input)
 //   A layer's input is one or two segments of this space (LayerDesc), so the skip concat
 //   [E_s | h] (neddf.py:217-219) and the colour concat need no data movement.
-// Weights: packed once per optimiser step into [k_pad][256] fp32 with the channel permutation
-//   above, streamed layer by layer in 16-row (16 KB) chunks through a 3-stage shared-memory
+// Weights: packed once per optimiser step into [k_pad][256] fp32 with a channel permutation
+//   that makes every thread's 16 weights four conflict-free LDS.128 (see abi.cu simt_col), streamed layer by layer in 16-row (16 KB) chunks through a 3-stage shared-memory
 //   ring by the TMA bulk-copy engine (cp.async.bulk + mbarrier complete_tx); the whole model
 //   (2.6 MB) stays L2-resident.
 #include "field_math.cuh"
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_simt_kernel(const __grid_co
       for (int c = 0; c < n_chunks; ++c, ++g) {
         const int stage = (int)(g % kStages);
         mbar_wait(&full[stage], (uint32_t)((g / kStages) & 1));
-        const float* wchunk = wst + stage * kChunkFloats + cg * 16;
+        const float* wchunk = wst + stage * kChunkFloats + cg * 4;
         const int r0 = c * kChunkRows;
         const int rows = min(kChunkRows, L.k_in - r0);
 #pragma unroll 4
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_simt_kernel(const __grid_co
           float w[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float4 t = wp[q];
+            float4 t = wp[q * 16];  // q*64 floats: lanes of a half-warp read 256 contiguous bytes
             w[4 * q + 0] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
           }
 #pragma unroll
@@ -219,11 +219,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_simt_kernel(const __grid_co
       }
 
       // epilogue: bias + activation with Jacobian, written back in place (h region)
-      const float* bias = p.b_hidden + L.bias_off + cg * 16;
+      const float* bias = p.b_hidden + L.bias_off + cg * 4;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float y, d1;
-        hidden_act<ACT>(acc[0][i] + __ldg(bias + i), y, d1);
+        hidden_act<ACT>(acc[0][i] + __ldg(bias + (i >> 2) * 64 + (i & 3)), y, d1);
         const int ch = cg + 16 * i;
         *reinterpret_cast<float4*>(&act[(size_t)(p.off_h + ch) * kPitch + 4 * s_slot]) =
             make_float4(y, d1 * acc[1][i], d1 * acc[2][i], d1 * acc[3][i]);

@@ -249,6 +249,9 @@ class NeDDF(BaseNeuralField):
         """Same network with the sample geometry fused into the kernel prologue (no [N,3]
         Sampling tensors in HBM).  Used by NeRFRender."""
         self._check_no_grad()
+        ray_dir = L.require_cuda_f32(ray_dir, "ray_dir")
+        ray_orig = L.require_cuda_f32(ray_orig, "ray_orig")
+        dists = L.require_cuda_f32(dists, "dists")
         B, S = dists.shape
         device = dists.device
         out = {
@@ -277,6 +280,20 @@ class NeDDF(BaseNeuralField):
             e1.record(torch.cuda.current_stream(device))
             prof.append((e0, e1, B * S))
         return out
+
+    def check_engine_status(self) -> None:
+        """Read-and-clear the engine's device status word (one sync).  Raises if the tensor-core
+        engine met an activation outside fp16 range (its operands are fp16 hi+lo pairs)."""
+        if self._handle is None:
+            return
+        v = C.c_int32(0)
+        dev = self._handle_device
+        with torch.cuda.device(dev):
+            L.check(L.lib().neddf_field_status(self._handle, C.byref(v), L.stream_ptr(dev)), "field_status")
+        if v.value & 4:
+            raise FloatingPointError(
+                "neddf_b200: tensor-core engine saw |activation| > 65504 (fp16 range of its split operands); "
+                "results of the last calls are invalid - use set_engine('fp32') for this network")
 
     def set_iter(self, iter: int) -> None:
         """Warm-up schedule (neddf.py:311-326); -1 = evaluation."""

@@ -143,6 +143,10 @@ class BaseNeuralRender(nn.Module):
         """The reference asserts `not any(isnan(w))` inside integrate_volume_render
         (base_neural_render.py:155) - a host sync per call.  The kernels record the condition in
         a device flag instead; this reads it (one sync) and raises like the reference."""
+        for net in {id(n): n for n in (getattr(self, "network_coarse", None), getattr(self, "network_fine", None))
+                    if n is not None}.values():
+            if hasattr(net, "check_engine_status"):
+                net.check_engine_status()
         st = getattr(self, "_status_buf", None)
         if st is None:
             return

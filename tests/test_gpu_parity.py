@@ -13,12 +13,31 @@ from oracle import neddf_oracle as orc  # noqa: E402
 from tests.helpers import PARITY_TOL, Case, assert_parity, nerr  # noqa: E402
 
 CASES = ["bunny", "default", "point", "leaky"]
-ENGINES = ["fp32"]
+ENGINES = ["fp32", "tc"]
 
 
 def _gpu():
     import tests.gpu_util as G
     return G
+
+
+@pytest.mark.parametrize("n,k", [(128, 16), (128, 64), (128, 128), (16, 16), (16, 256)])
+def test_tc_selftest_gemm(n, k):
+    """tcgen05 building block (descriptor layouts, fp16-split 3-product accumulation) against an
+    fp64 GEMM: hidden configuration (n=128) and head configuration (n=16)."""
+    G = _gpu()
+    from neddf_b200 import _lib as L
+    g = torch.Generator().manual_seed(n * 1000 + k)
+    a = torch.randn(128, k, generator=g)
+    b = torch.randn(n, k, generator=g)
+    a[3, 5 % k] = 300.0  # exercise a large magnitude (fp16 hi + lo)
+    ad, bd = a.to(G.DEV), b.to(G.DEV)
+    c = torch.full((128, n), float("nan"), device=G.DEV)
+    L.check(L.lib().neddf_tc_selftest(L.ptr(ad), L.ptr(bd), 128, n, k, L.ptr(c), L.stream_ptr(G.DEV)), "tc_selftest")
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().T
+    err = float((c.cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, err
 
 
 def test_make_rays_and_samples():
@@ -189,6 +208,7 @@ def test_render_rays_matches_reference(name, engine):
     for k, v in ref.items():
         assert tuple(out[k].shape) == v.shape, k
         assert_parity(out[k].cpu().numpy(), v, PARITY_TOL, c.kinked, k)
+    render.network_fine.check_engine_status()
 
 
 @pytest.mark.parametrize("engine", ENGINES)
