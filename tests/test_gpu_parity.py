@@ -166,6 +166,11 @@ def test_field_forward_matches_reference(name, engine):
         out = render.network_fine(neddf_b200.Sampling(pos.to(G.DEV), dd.contiguous().to(G.DEV), var.to(G.DEV)))
     for k in ("distance", "density", "color", "fields_penalty", "aux_grad"):
         assert_parity(out[k].cpu().numpy(), c.z["field_fine_" + k], PARITY_TOL, c.kinked, k)
+    # ... and composited on the same fine distances it reproduces the reference's render outputs,
+    # per-sample weights included
+    comp = render.integrate_volume_render(c.t("dists_fine").to(G.DEV), out["density"], out["color"], out["fields_penalty"])
+    for k in ("weight", "depth", "color", "transmittance", "fields_penalty"):
+        assert_parity(comp[k].cpu().numpy(), c.z["out_" + k], PARITY_TOL, c.kinked, k)
     # fused-geometry entry point gives the same numbers
     with torch.no_grad():
         out2 = render.network_fine.forward_rays(d_ref.to(G.DEV), o_ref.to(G.DEV).contiguous(), c.t("dists_fine").to(G.DEV),
@@ -207,7 +212,13 @@ def test_render_rays_matches_reference(name, engine):
     assert set(out.keys()) == set(ref.keys())
     for k, v in ref.items():
         assert tuple(out[k].shape) == v.shape, k
-        assert_parity(out[k].cpu().numpy(), v, PARITY_TOL, c.kinked, k)
+        # End to end, the per-sample fine `weight` is compared at positions that were themselves
+        # resampled from the coarse weights: a 1e-6 change of a coarse weight moves fine samples,
+        # and where two samples nearly coincide the interval width (hence the weight) moves by
+        # far more in relative terms.  The integrated outputs keep the 1e-4 bound; the per-sample
+        # weights are pinned at 1e-4 stage-wise (test_field_forward_matches_reference).
+        tol = 1e-3 if k == "weight" else PARITY_TOL
+        assert_parity(out[k].cpu().numpy(), v, tol, c.kinked, k)
     render.network_fine.check_engine_status()
 
 
