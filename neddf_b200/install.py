@@ -1,0 +1,29 @@
+"""Make the reference's own scripts pick up the B200 renderer without editing them.
+
+``neddf/scripts/run_eval.py`` re-composes the *saved* hydra config, whose ``_target_`` strings are
+always ``neddf.render.NeRFRender`` / ``neddf.network.NeDDF``.  Hydra resolves
+those dotted paths by attribute lookup at instantiate time, so rebinding the two attributes on
+the already-imported reference package is enough:
+
+    import neddf_b200.install; neddf_b200.install.install()
+
+or, without touching any file of the reference:
+
+    python -m neddf_b200.launch neddf/scripts/run_eval.py pretrained/bunny_smoke
+"""
+import importlib
+
+
+def install() -> None:
+    import neddf_b200
+
+    ref_render = importlib.import_module("neddf.render")
+    ref_network = importlib.import_module("neddf.network")
+    ref_render.NeRFRender = neddf_b200.NeRFRender
+    ref_network.NeDDF = neddf_b200.NeDDF
+    for mod, name, obj in (("neddf.render.nerf_render", "NeRFRender", neddf_b200.NeRFRender),
+                           ("neddf.network.neddf", "NeDDF", neddf_b200.NeDDF)):
+        try:
+            setattr(importlib.import_module(mod), name, obj)
+        except Exception:
+            pass

@@ -28,7 +28,7 @@ def assert_parity(new, ref, tol, kinked=False, what=""):
     crosses 0, so two fp32 evaluations that differ only in summation order legitimately
     disagree by O(1e-4..1e-3) on the handful of samples that sit within rounding distance of
     a kink (the reference disagrees with its own fp64 run there).  For those configs the bound
-    is applied to all but 1% of the elements and the outliers are capped at 5e-2."""
+    is applied to all but 1% of the elements (at least 2) and the outliers are capped at 5e-2."""
     new = np.asarray(new, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert new.shape == ref.shape, (what, new.shape, ref.shape)
@@ -37,8 +37,8 @@ def assert_parity(new, ref, tol, kinked=False, what=""):
     if not kinked:
         assert float(err.max()) < tol, (what, float(err.max()))
         return
-    frac = float((err >= tol).mean())
-    assert frac <= 1e-2 and float(err.max()) < 5e-2, (what, frac, float(err.max()))
+    n_out = int((err >= tol).sum())
+    assert n_out <= max(2, int(1e-2 * err.size)) and float(err.max()) < 5e-2, (what, n_out, err.size, float(err.max()))
 
 
 class Case:

@@ -59,3 +59,24 @@ def test_camera_standin_matches_reference_pose():
     cam2 = neddf_b200.Camera(neddf_b200.PinholeCalib([100, 100, 50, 50]), np.concatenate([rv, [1, 2, 3]]))
     assert np.allclose(cam2.R.numpy(), Rotation.from_rotvec(rv).as_matrix(), atol=1e-6)
     assert np.allclose(cam2.T.numpy(), [1, 2, 3])
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/neddf"), reason="reference tree not present")
+def test_install_rebinds_reference_targets(repo_root):
+    """neddf_b200.install makes the saved `_target_` strings resolve to the B200 classes and the
+    pretrained checkpoint loads unchanged (subprocess: do not pollute this interpreter's modules)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, yaml, torch, hydra\n"
+        "import neddf_b200.install as I; I.install()\n"
+        "cfg = yaml.safe_load(open('/root/reference/pretrained/bunny_smoke/.hydra/config.yaml'))\n"
+        "r = hydra.utils.instantiate(dict(cfg['render']), network_config=cfg['network'])\n"
+        "assert type(r).__module__ == 'neddf_b200.render' and type(r.network_fine).__module__ == 'neddf_b200.network'\n"
+        "res = r.load_state_dict(torch.load('/root/reference/pretrained/bunny_smoke/models/model_02000.pth', map_location='cpu'))\n"
+        "assert not res.missing_keys and not res.unexpected_keys\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(["/root/reference", os.path.join(repo_root, "tests/golden/_refstub"), repo_root]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
