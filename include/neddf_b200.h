@@ -110,6 +110,11 @@ int32_t neddf_field_resolve_engine(const neddf_field_t* f, int32_t engine);
  * invalid and the caller should use NEDDF_ENGINE_FP32 for this network. */
 int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* stream);
 
+/* Profiling aid for the tensor-core engine: when d_buf != NULL, CTA 0 of every following launch
+ * writes 4 SM-clock stamps per (tile, step) into d_buf[capacity] (int64): MMA phase start, MMA
+ * issue done, epilogue start, epilogue done.  Pass NULL to switch it off. */
+int32_t neddf_field_set_timeline(neddf_field_t* f, int64_t* d_buf, int32_t capacity);
+
 /* Re-pack the module's parameters into kernel layout.  d_weights[i] is the i-th layer's
  * weight, fp32 [in,out] row-major exactly as LinearGradLayer stores it
  * (nn_module/with_grad/linear.py:111-116); d_biases[i] its bias [out].  Must be called
@@ -197,6 +202,12 @@ int64_t neddf_launch_count(void);
  * operands; returns 0 and fills d_c.  Used by tests to pin the UMMA descriptor layouts. */
 int32_t neddf_tc_selftest(const float* d_a, const float* d_b, int32_t m, int32_t n, int32_t k,
                           float* d_c, void* stream);
+
+/* tcgen05 issue-rate microbenchmark (profiling aid): reps x 16 MMAs 128 x n x 16 on resident
+ * shared-memory operands; a_mn / b_mn = 1 for MN-major operands, swizzle 0 (none) or 2 (128B).
+ * d_cycles[0] = SM cycles to issue, d_cycles[1] = cycles until the last MMA completed. */
+int32_t neddf_tc_mma_bench(int32_t a_mn, int32_t b_mn, int32_t swizzle, int32_t n, int32_t reps,
+                           int64_t* d_cycles, void* stream);
 
 #ifdef __cplusplus
 }

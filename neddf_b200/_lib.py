@@ -50,6 +50,7 @@ _SIGNATURES = {
     "neddf_field_create": (_I32, [C.POINTER(FieldConfig), C.POINTER(_P)]),
     "neddf_field_destroy": (_I32, [_P]),
     "neddf_field_resolve_engine": (_I32, [_P, _I32]),
+    "neddf_field_set_timeline": (_I32, [_P, _P, _I32]),
     "neddf_field_status": (_I32, [_P, C.POINTER(C.c_int32), _P]),
     "neddf_field_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P]),
     "neddf_make_rays": (_I32, [_P, _I32, _I64, _FP, _FP, _FP, _P, _P, _P]),
@@ -62,6 +63,7 @@ _SIGNATURES = {
     "neddf_composite": (_I32, [_P, _P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P, _P]),
     "neddf_sample_pdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "neddf_invert_cdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "neddf_tc_mma_bench": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _P]),
     "neddf_tc_selftest": (_I32, [_P, _P, _I32, _I32, _I32, _P, _P]),
 }
 

@@ -222,6 +222,12 @@ extern "C" int32_t neddf_field_resolve_engine(const neddf_field_t* f, int32_t en
   return engine;
 }
 
+extern "C" int32_t neddf_field_set_timeline(neddf_field_t* f, int64_t* d_buf, int32_t capacity) {
+  if (!f) return fail(NEDDF_E_INVALID, "neddf_field_set_timeline: field is NULL");
+  if (!tc_supported(f)) return fail(NEDDF_E_UNSUPPORTED, "timeline is a tensor-core engine facility");
+  return tc_set_timeline(f, reinterpret_cast<long long*>(d_buf), capacity);
+}
+
 extern "C" int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* stream) {
   if (!f || !h_status_out) return fail(NEDDF_E_INVALID, "neddf_field_status: NULL argument");
   int v = 0;

@@ -89,5 +89,6 @@ int32_t tc_pack_weights(neddf_field* f, const float* const* d_w, const float* co
 int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStream_t s);
 bool tc_supported(const neddf_field* f);
 void tc_destroy(neddf_field* f);
+int32_t tc_set_timeline(neddf_field* f, long long* d_buf, int cap);
 int32_t tc_read_status(const neddf_field* f, int* out, cudaStream_t s);
 }  // namespace neddf

@@ -20,21 +20,24 @@
 // The narrow heads (256->1,1,3) run in the standard orientation (A = activations, N = 16) so that
 // their result has one sample row per lane.
 //
-// Per SM: one CTA of 10 warps, persistent over 32-sample tiles.
-//   warps 0-7  epilogue: TMEM -> registers (tcgen05.ld), bias + activation + Jacobian, fp16
-//              hi/lo split, st.shared into the next B operand; also prologue (geometry, PE)
-//   warp  8    TMA producer: cp.async.bulk of 8 KB weight chunks through a 5-stage ring
-//   warp  9    MMA issuer: one thread, tcgen05.mma + tcgen05.commit onto mbarriers
+// Per SM: one CTA of 18 warps, persistent over 32-sample tiles.
+//   warps 0-15 epilogue: TMEM -> registers (tcgen05.ld), bias + activation + Jacobian, fp16
+//              hi/lo split, st.shared into the next B operand; also prologue (geometry, PE).
+//              warp w: TMEM lane quarter w%4, channel half (w/4)%2, sample half w/8
+//   warp  16   TMA producer: cp.async.bulk of 8 KB weight chunks through a 5-stage ring
+//   warp  17   MMA issuer: one thread, tcgen05.mma + tcgen05.commit onto mbarriers
 // Shared memory (B operands, canonical no-swizzle MN-major: [row/8][k][row%8] fp16):
 //   H   hi/lo  128 rows x 256 k   2 x 64 KB   hidden activations, rewritten layer after layer
 //   AUX hi/lo  128 rows x  96 k   2 x 24 KB   E_s (trunk input + skip) then [E0|D|n] (colour input)
 //   W ring     5 x 8 KB                      weight chunks [hi 4 KB | lo 4 KB], K-major
-// TMEM: cols [0,128) channels 0-127, [128,256) channels 128-255, [256,272) head results.
+// TMEM: channel half h at columns [256h, 256h+256): [0,128) = A_hi*B_hi + A_lo*B_hi, [128,256) =
+// A_hi*B_lo (summed in the epilogue); head results alias columns [0,16).
 #include "field_math.cuh"
 
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace neddf {
@@ -46,12 +49,12 @@ constexpr int kHK = 256;                // K capacity of H
 constexpr int kAuxK = 96;               // K capacity of AUX
 constexpr int kStageBytes = 8192;
 constexpr int kNumStages = 5;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;
 constexpr int kMaxSteps = kMaxHidden + 2;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kHeadCol = 256;
+constexpr uint32_t kHeadCol = 0;  // head results alias the (then idle) hidden accumulators
 
 constexpr uint32_t kHBytes = kRows * kHK * 2;      // 65536 per hi / lo
 constexpr uint32_t kAuxBytes = kRows * kAuxK * 2;  // 24576 per hi / lo
@@ -74,6 +77,8 @@ struct Scratch {
 };
 constexpr uint32_t kSmemBytes = kOffScratch + sizeof(Scratch);
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kOffHLo == kOffHHi + 16 * (kHK * 16) && kOffAuxLo == kOffAuxHi + 16 * (kAuxK * 16),
+              "lo buffers must follow the hi buffers at exactly 16 row-groups (wide-N MMA)");
 
 enum StepKind { kStepHidden = 0, kStepHeadDA = 1, kStepHeadCol = 2 };
 
@@ -82,6 +87,8 @@ struct Step {
   int aux_ksteps;  // K-steps (16) taken from AUX first ...
   int h_ksteps;    // ... then from H
   int bias_off;    // hidden layers: offset into the plain-order bias array
+  int post;        // work the epilogue warps do after this step's epilogue, overlapping the next
+                   // step's MMA phase: 1 = colour-trunk inputs E0|D into AUX, 2 = next tile's prologue
 };
 
 struct TcParams {
@@ -92,6 +99,10 @@ struct TcParams {
   const unsigned char* w_tc;  // packed chunks, kStageBytes each, in consumption order
   const float* bias;          // [n_hidden][256] plain channel order
   int* status;
+  int debug;            // profiling experiments: bit0 = no weight refills (results invalid)
+  int cluster;          // CTAs per cluster sharing one multicast weight stream (1, 2 or 4)
+  long long* timeline;  // optional: CTA 0 writes 6 values per step (profiling aid)
+  int timeline_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -143,6 +154,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// multicast variant: the chunk lands at the same offset in every CTA of `mask`, and each of
+// those CTAs' own barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -170,7 +199,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
   return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
-constexpr uint32_t kIdescHidden = make_idesc(128, kRows, 0, 1);  // A weights K-major, B activations MN-major
+constexpr uint32_t kIdescHidden = make_idesc(128, kRows, 0, 1);      // A weights K-major, B activations MN-major
+// B = [hi rows | lo rows]: the lo buffer starts exactly 16 row-groups after the hi buffer, so one
+// N = 256 MMA produces A_hi*B_hi (columns 0-127) and A_hi*B_lo (columns 128-255) together
+constexpr uint32_t kIdescHiddenWide = make_idesc(128, 2 * kRows, 0, 1);
 constexpr uint32_t kIdescHead = make_idesc(kRows, 16, 1, 0);     // A activations MN-major, B head weights K-major
 
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -182,6 +214,48 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-uniform variants: the whole warp executes them with identical operands and one elected
+// lane issues.  Keeping the issuing code convergent lets ptxas hold descriptors in uniform
+// registers; under `if (lane == 0)` it wraps every UTCHMMA in an ELECT/R2UR.BROADCAST loop.
+__device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc_elect(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -213,19 +287,60 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// tanhExp with first derivative on the SFU (MUFU.EX2 x2 + MUFU.RCP), ~20 instructions instead of
+// ~55 for expf + tanhf.  e^x carries the rounding residual of x*log2(e) (relative error ~2e-7);
+// tanh(u), u = e^x >= 0, is 1 - 2/(e^{2u}+1) for u >= 1/8 (absolute error ~1.2e-7) and its odd
+// series below (truncation < 2e-9), so y and f' stay within a few fp32 ulp of the reference's
+// libm evaluation in absolute terms.  Same masks as nn_module/with_grad/tanh_exp.py:38-45.
+__device__ __forceinline__ void tanhexp_fast(float x, float& y, float& d1) {
+  const float kL2E = 1.4426950408889634f, kL2E_lo = 1.9259629911266175e-8f, kLn2 = 0.6931471805599453f;
+  float t = x * kL2E;
+  float r = fmaf(x, kL2E, -t) + x * kL2E_lo;  // what rounding t dropped
+  float ex = ex2_approx(t);
+  ex = fmaf(ex, r * kLn2, ex);
+  float E = ex2_approx(ex * (2.0f * kL2E));
+  float tx_big = fmaf(-2.0f, rcp_approx(E + 1.0f), 1.0f);
+  float u2 = ex * ex;
+  float poly = fmaf(u2, fmaf(u2, fmaf(u2, -17.0f / 315.0f, 2.0f / 15.0f), -1.0f / 3.0f), 1.0f);
+  float tx = (ex < 0.125f) ? ex * poly : tx_big;
+  float yy = x * tx;
+  float dd = tx - x * ex * (tx * tx - 1.0f);
+  const bool big = x > 20.0f;
+  y = big ? x : yy;
+  d1 = big ? 1.0f : dd;
+}
+
+template <int ACT>
+__device__ __forceinline__ void tc_hidden_act(float x, float& y, float& d1) {
+  if (ACT == NEDDF_ACT_TANHEXP) tanhexp_fast(x, y, d1);
+  else hidden_act<ACT>(x, y, d1);
+}
+
 // x = hi + lo with hi, lo fp16 (round to nearest); returns packed pairs and flags fp16 overflow
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo, uint32_t& bad) {
+// `amax` tracks max |value| (fp16 range check, one FMNMX per value; NaN shows up in the outputs)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo, float& amax) {
   __half2 h = __floats2half2_rn(a, b);
   float2 hf = __half22float2(h);
   __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
-  bad |= ((hi & 0x7c00u) == 0x7c00u) | ((hi & 0x7c000000u) == 0x7c000000u);
+  amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
 }
 
 // write the 4 rows (value, Jx, Jy, Jz) of sample s, K index k into an operand buffer pair
 __device__ __forceinline__ void store_sample(unsigned char* hi_buf, unsigned char* lo_buf, int KC, int s, int k,
-                                             float v0, float v1, float v2, float v3, uint32_t& bad) {
+                                             float v0, float v1, float v2, float v3, float& bad) {
   uint32_t h0, l0, h1, l1;
   split2(v0, v1, h0, l0, bad);
   split2(v2, v3, h1, l1, bad);
@@ -274,7 +389,7 @@ __device__ __forceinline__ void tile_geometry(const FieldParams& p, Scratch* sc,
 // (neddf.py:200-204) else plain (neddf.py:205-209).  `sub`/`nsub` split the 3*E entries.
 __device__ __forceinline__ void write_pos_embedding(const FieldParams& p, const Scratch* sc, unsigned char* aux_hi,
                                                     unsigned char* aux_lo, int s, int sub, int nsub, bool scaled,
-                                                    uint32_t& bad) {
+                                                    float& bad) {
   const int half = 3 * p.embed_pos;
   for (int idx = sub; idx < half; idx += nsub) {
     int e = idx / 3, d = idx - 3 * e;
@@ -308,111 +423,152 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
+  // Tiles are handed out in groups of `cluster` consecutive tiles, one group per cluster per
+  // round, so that all CTAs of a cluster run the same number of tiles (they share one multicast
+  // weight stream and must consume it in lockstep).  A CTA whose tile index is past the end
+  // computes a dummy tile (no valid samples, nothing written).
+  const int CL = P.cluster;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   const int64_t n_tiles = (p.n + kTileS - 1) / kTileS;
+  const int64_t n_groups = (n_tiles + CL - 1) / CL;
+  const int64_t cid = blockIdx.x / CL, n_clusters = gridDim.x / CL;
   int64_t my_tiles = 0;
-  if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - blockIdx.x) / gridDim.x + 1;
+  if (cid < n_groups) my_tiles = (n_groups - 1 - cid) / n_clusters + 1;
   const int64_t total_chunks = my_tiles * P.chunks_per_tile;
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   if (tid == 0) {
     for (int i = 0; i < kNumStages; ++i) {
       mbar_init(&sc->full[i], 1);
-      mbar_init(&sc->empty[i], 1);
+      mbar_init(&sc->empty[i], CL);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     mbar_init(&sc->act_ready, kEpiThreads);
     mbar_init(&sc->acc_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) tmem_alloc(&sc->tmem_base, kTmemCols);
+  if (warp == kEpiWarps + 1) tmem_alloc(&sc->tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = sc->tmem_base;
 
-  if (warp == 8) {
+  if (warp == kEpiWarps) {
     // ===================== TMA producer =====================================================
-    if (lane == 0) {
+    if (lane == 0 && !(P.debug & 1)) {
+      int stage = 0, cidx = 0;
+      uint32_t par = 0;  // parity of the previous use's phase of empty[]; the first pass does not wait
+      bool first_pass = true;
       for (int64_t g = 0; g < total_chunks; ++g) {
-        const int stage = (int)(g % kNumStages);
-        if (g >= kNumStages) mbar_wait(&sc->empty[stage], (uint32_t)(((g / kNumStages) - 1) & 1));
+        if (!first_pass) mbar_wait(&sc->empty[stage], par);
         mbar_expect_tx(&sc->full[stage], kStageBytes);
-        bulk_g2s(stages + stage * kStageBytes, P.w_tc + (size_t)(g % P.chunks_per_tile) * kStageBytes, kStageBytes,
-                 &sc->full[stage]);
+        const unsigned char* src = P.w_tc + (size_t)cidx * kStageBytes;
+        if (CL == 1) {
+          bulk_g2s(stages + stage * kStageBytes, src, kStageBytes, &sc->full[stage]);
+        } else if ((uint32_t)(cidx % CL) == crank) {
+          // this CTA fetches the chunk for the whole cluster: one L2 read, CL shared-memory copies
+          // (chunks_per_tile is even, so cidx % CL == g % CL for CL in {2,4} when it divides it)
+          bulk_g2s_mc(stages + stage * kStageBytes, src, kStageBytes, &sc->full[stage], cmask);
+        }
+        if (++cidx == P.chunks_per_tile) cidx = 0;
+        if (++stage == kNumStages) {
+          stage = 0;
+          if (first_pass) first_pass = false;
+          else par ^= 1;
+        }
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer ========================================================
-    if (lane == 0) {
-      const uint32_t s_hhi = smem_u32(h_hi), s_hlo = smem_u32(h_lo);
-      const uint32_t s_ahi = smem_u32(aux_hi), s_alo = smem_u32(aux_lo);
-      const uint32_t s_stage = smem_u32(stages);
-      int64_t g = 0;
-      uint32_t act_phase = 0;
-      for (int64_t t = 0; t < my_tiles; ++t) {
-        for (int si = 0; si < P.n_steps; ++si) {
-          const Step& st = P.step[si];
-          mbar_wait(&sc->act_ready, act_phase);
-          act_phase ^= 1;
-          tc_fence_after();
-          if (st.kind == kStepHidden) {
-            const int ksteps = st.aux_ksteps + st.h_ksteps;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              uint32_t b_hi, b_lo, sbo;
-              if (ks < st.aux_ksteps) {
-                b_hi = s_ahi + ks * 256;
-                b_lo = s_alo + ks * 256;
-                sbo = kAuxK * 16;
-              } else {
-                b_hi = s_hhi + (ks - st.aux_ksteps) * 256;
-                b_lo = s_hlo + (ks - st.aux_ksteps) * 256;
-                sbo = kHK * 16;
-              }
-              const uint64_t db_hi = make_desc(b_hi, 128, sbo), db_lo = make_desc(b_lo, 128, sbo);
+  } else if (warp == kEpiWarps + 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) ===================
+    const uint32_t s_hhi = smem_u32(h_hi), s_ahi = smem_u32(aux_hi), s_hlo = smem_u32(h_lo);
+    const uint32_t s_stage = smem_u32(stages);
+    const uint64_t da0 = make_desc(s_stage, 128, 256);
+    int stage = 0;          // ring position of the next chunk
+    uint32_t full_par = 0;  // parity to wait for on full[stage]
+    uint32_t act_phase = 0;
+    auto advance = [&]() {
+      if (++stage == kNumStages) {
+        stage = 0;
+        full_par ^= 1;
+      }
+    };
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      for (int si = 0; si < P.n_steps; ++si) {
+        const Step& st = P.step[si];
+        mbar_wait(&sc->act_ready, act_phase);
+        act_phase ^= 1;
+        tc_fence_after();
+        const int tl = (int)(t * P.n_steps + si);
+        const bool stamp = P.timeline && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
+        if (stamp) P.timeline[6 * tl + 0] = clock64();
+        if (st.kind == kStepHidden) {
+          // Per K-step and channel half one 8 KB chunk [A_hi | A_lo] and two MMAs:
+          //   cols [0,128)   += A_hi*B_hi + A_lo*B_hi,   cols [128,256) += A_hi*B_lo
+          // (B = [hi rows | lo rows] as one N = 256 operand).  tcgen05.mma issue is not free -
+          // every instruction between two MMAs lengthens the phase (tools/mma_bench.py) - so ring
+          // positions are counters (no 64-bit div/mod) and descriptors advance by one add.
+          const int ksteps = st.aux_ksteps + st.h_ksteps;
+          uint64_t db = make_desc(st.aux_ksteps ? s_ahi : s_hhi, 128, st.aux_ksteps ? kAuxK * 16 : kHK * 16);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            if (ks == st.aux_ksteps && ks > 0) db = make_desc(s_hhi, 128, kHK * 16);
+            const uint32_t acc = ks > 0;
 #pragma unroll
-              for (int half = 0; half < 2; ++half, ++g) {
-                const int stage = (int)(g % kNumStages);
-                mbar_wait(&sc->full[stage], (uint32_t)((g / kNumStages) & 1));
-                tc_fence_after();
-                const uint32_t a = s_stage + stage * kStageBytes;
-                const uint64_t da_hi = make_desc(a, 128, 256), da_lo = make_desc(a + 4096, 128, 256);
-                const uint32_t d = tmem + half * kRows;
-                mma_f16(d, da_hi, db_hi, kIdescHidden, ks > 0);
-                mma_f16(d, da_lo, db_hi, kIdescHidden, 1);
-                mma_f16(d, da_hi, db_lo, kIdescHidden, 1);
-                mma_commit(&sc->empty[stage]);
-              }
+            for (int half = 0; half < 2; ++half) {
+              if (!(P.debug & 1)) mbar_wait(&sc->full[stage], full_par);
+              tc_fence_after();
+              const uint64_t a = da0 + (uint64_t)(stage * (kStageBytes >> 4));
+              const uint32_t d = tmem + half * (2 * kRows);
+              mma_f16_elect(d, a, db, kIdescHiddenWide, acc);
+              mma_f16_elect(d, a + (4096 >> 4), db, kIdescHidden, 1);
+              if (CL == 1) mma_commit_elect(&sc->empty[stage]);
+              else mma_commit_mc_elect(&sc->empty[stage], cmask);
+              advance();
             }
-          } else {
-            // heads: D[row, n] = sum_k H[row,k] * Wh[n,k]; chunk g = hi, g+1 = lo
-            const int st0 = (int)(g % kNumStages), st1 = (int)((g + 1) % kNumStages);
-            mbar_wait(&sc->full[st0], (uint32_t)((g / kNumStages) & 1));
-            mbar_wait(&sc->full[st1], (uint32_t)(((g + 1) / kNumStages) & 1));
-            tc_fence_after();
-            const uint32_t w_hi = s_stage + st0 * kStageBytes, w_lo = s_stage + st1 * kStageBytes;
-            const uint32_t d = tmem + kHeadCol;
-            for (int ks = 0; ks < kHK / 16; ++ks) {
-              const uint64_t da_hi = make_desc(s_hhi + ks * 256, 128, kHK * 16);
-              const uint64_t da_lo = make_desc(s_hlo + ks * 256, 128, kHK * 16);
-              const uint64_t db_hi = make_desc(w_hi + ks * 256, 128, 4096);
-              const uint64_t db_lo = make_desc(w_lo + ks * 256, 128, 4096);
-              mma_f16(d, da_hi, db_hi, kIdescHead, ks > 0);
-              mma_f16(d, da_lo, db_hi, kIdescHead, 1);
-              mma_f16(d, da_hi, db_lo, kIdescHead, 1);
-            }
-            mma_commit(&sc->empty[st0]);
-            mma_commit(&sc->empty[st1]);
-            g += 2;
+            db += 256 >> 4;  // next K-step: 16 k x 16 bytes
           }
-          mma_commit(&sc->acc_ready);
+        } else {
+          // heads: D[row, n] = sum_k H[row,k] * Wh[n,k]; two chunks: hi then lo head weights
+          const int st0 = stage;
+          const uint32_t p0 = full_par;
+          advance();
+          const int st1 = stage;
+          const uint32_t p1 = full_par;
+          advance();
+          if (!(P.debug & 1)) {
+            mbar_wait(&sc->full[st0], p0);
+            mbar_wait(&sc->full[st1], p1);
+          }
+          tc_fence_after();
+          const uint32_t w_hi = s_stage + st0 * kStageBytes, w_lo = s_stage + st1 * kStageBytes;
+          const uint32_t d = tmem + kHeadCol;
+          uint64_t da_hi = make_desc(s_hhi, 128, kHK * 16), da_lo = make_desc(s_hlo, 128, kHK * 16);
+          uint64_t db_hi = make_desc(w_hi, 128, 4096), db_lo = make_desc(w_lo, 128, 4096);
+          for (int ks = 0; ks < kHK / 16; ++ks) {
+            mma_f16_elect(d, da_hi, db_hi, kIdescHead, ks > 0);
+            mma_f16_elect(d, da_lo, db_hi, kIdescHead, 1);
+            mma_f16_elect(d, da_hi, db_lo, kIdescHead, 1);
+            da_hi += 16; da_lo += 16; db_hi += 16; db_lo += 16;
+          }
+          if (CL == 1) {
+            mma_commit_elect(&sc->empty[st0]);
+            mma_commit_elect(&sc->empty[st1]);
+          } else {
+            mma_commit_mc_elect(&sc->empty[st0], cmask);
+            mma_commit_mc_elect(&sc->empty[st1], cmask);
+          }
         }
+        mma_commit_elect(&sc->acc_ready);
+        if (stamp) P.timeline[6 * tl + 1] = clock64();
       }
     }
   } else {
     // ===================== epilogue warps =====================================================
-    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
-    const int half = warp >> 2;     // accumulator half (channels 128*half ..)
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp >> 2) & 1;    // accumulator half (channels 128*half ..)
+    const int shalf = warp >> 3;         // which 16 samples (64 columns) of the tile this warp handles
     const int ch = 128 * half + 32 * quarter + lane;
     const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
-    uint32_t bad = 0;
+    float bad = 0.f;  // max |operand value| seen (fp16 range check)
     uint32_t acc_phase = 0;
 
     // prologue of the first tile
@@ -420,37 +576,61 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
       const int64_t n0 = tile * kTileS;
       if (tid < kTileS) tile_geometry(p, sc, n0, tid);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      const int s = tid >> 3, sub = tid & 7;
-      write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 8, true, bad);
+      const int s = tid >> 4, sub = tid & 15;
+      write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 16, true, bad);
       // zero the K padding of E_s (its weights are zero, the operand must still be finite)
-      for (int k = p.n_e0 + sub; k < 64; k += 8) store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
+      for (int k = p.n_e0 + sub; k < 64; k += 16) store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
+    };
+    // colour-trunk inputs E0 | D (| zero pad) into AUX (neddf.py:205-210, 243); 16 threads per sample
+    auto colour_prep = [&]() {
+      const int s = tid >> 4, sub = tid & 15;
+      write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 16, false, bad);
+      const int dhalf = 3 * p.embed_dir;
+      for (int idx = sub; idx < dhalf; idx += 16) {
+        int e = idx / 3, d = idx - 3 * e;
+        float sn, cs;
+        sincosf((float)(1u << e) * sc->geo[s][3 + d], &sn, &cs);
+        store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + idx, sn, 0.f, 0.f, 0.f, bad);
+        store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + dhalf + idx, cs, 0.f, 0.f, 0.f, bad);
+      }
+      for (int k = p.n_e0 + p.n_d + 3 + sub; k < kAuxK; k += 16)
+        store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
     };
     if (my_tiles > 0) {
-      prologue(blockIdx.x);
+      prologue(cid * CL + crank);
       fence_async_smem();
       mbar_arrive(&sc->act_ready);
     }
 
     for (int64_t t = 0; t < my_tiles; ++t) {
-      const int64_t tile = blockIdx.x + t * gridDim.x;
+      const int64_t tile = (cid + t * n_clusters) * CL + crank;
       const int64_t n0 = tile * kTileS;
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.step[si];
-        mbar_wait(&sc->acc_ready, acc_phase);
+        // one thread polls the mbarrier; the other 511 sleep in a hardware named barrier instead of
+        // spinning on shared memory while the tensor core is streaming operands from it
+        if (tid == 0) mbar_wait(&sc->acc_ready, acc_phase);
+        asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
         acc_phase ^= 1;
         tc_fence_after();
+        const int tl = (int)(t * P.n_steps + si);
+        const bool stamp = P.timeline && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
+        if (stamp) P.timeline[6 * tl + 2] = clock64();
         if (st.kind == kStepHidden) {
           const float bias = __ldg(P.bias + st.bias_off + ch);
-          const uint32_t tbase = tmem + lane_addr + half * kRows;
+          const uint32_t tbase = tmem + lane_addr + half * (2 * kRows);
 #pragma unroll 1
-          for (int cb = 0; cb < kRows / 16; ++cb) {  // 16 columns = 4 samples per load
-            float v[16];
+          for (int cb = 4 * shalf; cb < 4 * shalf + 4; ++cb) {  // 16 columns = 4 samples per load
+            float v[16], v2[16];
             tmem_ld16(tbase + cb * 16, v);
+            tmem_ld16(tbase + kRows + cb * 16, v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += v2[i];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {  // 2 samples = one 16-byte row group
               float y0, d0, y1, d1;
-              hidden_act<ACT>(v[8 * q + 0] + bias, y0, d0);
-              hidden_act<ACT>(v[8 * q + 4] + bias, y1, d1);
+              tc_hidden_act<ACT>(v[8 * q + 0] + bias, y0, d0);
+              tc_hidden_act<ACT>(v[8 * q + 4] + bias, y1, d1);
               uint32_t h[4], l[4];
               split2(y0, d0 * v[8 * q + 1], h[0], l[0], bad);
               split2(d0 * v[8 * q + 2], d0 * v[8 * q + 3], h[1], l[1], bad);
@@ -483,22 +663,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
               for (int i = 0; i < 3; ++i) store_sample(aux_hi, aux_lo, kAuxK, s, kn + i, h.normal[i], 0.f, 0.f, 0.f, bad);
             }
-          } else {
-            // colour-trunk inputs E0 | D (| pad) into AUX while warps 0-3 finish the heads
-            const int t2 = tid - 128;
-            const int s = t2 >> 2, sub = t2 & 3;
-            write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 4, false, bad);
-            const int dhalf = 3 * p.embed_dir;
-            for (int idx = sub; idx < dhalf; idx += 4) {
-              int e = idx / 3, d = idx - 3 * e;
-              float sn, cs;
-              sincosf((float)(1u << e) * sc->geo[s][3 + d], &sn, &cs);
-              store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + idx, sn, 0.f, 0.f, 0.f, bad);
-              store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + dhalf + idx, cs, 0.f, 0.f, 0.f, bad);
-            }
-            for (int k = p.n_e0 + p.n_d + 3 + sub; k < kAuxK; k += 4)
-              store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
           }
+          if (st.post == 1) colour_prep();  // only when no earlier MMA phase could hide it
         } else {
           // colour head (neddf.py:257) + penalties (:259-300) + outputs, then next tile's prologue
           if (warp < 4) {
@@ -531,20 +697,24 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
               if (p.penalty) p.penalty[n] = field_penalty(h, col, colJ, p.distance_range_max, p.penalty_weight);
             }
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // scratch reads done
-          if (t + 1 < my_tiles) prologue(tile + gridDim.x);
         }
         tc_fence_before();
         fence_async_smem();
+        if (stamp) P.timeline[6 * tl + 3] = clock64();
         if (t + 1 < my_tiles || si + 1 < P.n_steps) mbar_arrive(&sc->act_ready);
+        // work that only feeds later steps runs here, under the next step's MMA phase; its
+        // shared-memory writes are published by the fence + arrive of the following steps
+        if (st.kind == kStepHidden && st.post == 1) colour_prep();
+        if (st.post == 2 && t + 1 < my_tiles) prologue(tile + n_clusters * CL);
       }
     }
-    if (bad && P.status) atomicOr(P.status, 4);
+    if (!(bad < 65504.0f) && P.status) atomicOr(P.status, 4);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, kTmemCols);
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
+  if (warp == kEpiWarps + 1) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -606,6 +776,13 @@ struct TcStorage {
   int chunks_per_tile = 0;
   Step step[kMaxSteps];
   TcPackArgs pack;
+  long long* timeline = nullptr;
+  int timeline_cap = 0;
+  // CTAs sharing one multicast weight stream.  Measured on B200: 1 -> 8.5k cycles per 256-K layer,
+  // 2 / 4 -> 11.9k / 11.6k (the lockstep coupling of the shared 5-stage ring costs more than the L2
+  // traffic it saves; the weight stream is not the bottleneck), so the default is 1.
+  // NEDDF_TC_CLUSTER=1|2|4 overrides.
+  int cluster = 1;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -626,7 +803,6 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool hidden = (n == kRows);
-  uint32_t bad = 0;
   // operands -> fp16 hi/lo in the kernel layouts
   for (int idx = tid; idx < 128 * k; idx += 128) {
     int kk = idx % k, r = idx / k;
@@ -653,7 +829,6 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
       *reinterpret_cast<__half*>(w_lo + hchunk_off(r, kk)) = lo;
     }
   }
-  (void)bad;
   if (tid == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -698,6 +873,76 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// ---------------------------------------------------------------------------------------------
+// MMA issue-rate microbenchmark: `reps` x 16 back-to-back MMAs on garbage operands in shared
+// memory, timed with clock64() between the first issue and the commit's arrival.
+//   a_mn, b_mn  : operand majorness (0 = K-major, 1 = MN-major)
+//   swz         : 0 = no swizzle (LBO 128), 2 = SWIZZLE_128B
+//   n           : MMA N (M is 128)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int a_mn, int b_mn, int swz, int n, int reps,
+                                                              long long* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar, bar2;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) mbar_init(&bar2, 1 << 20);
+  for (int i = tid; i < 49152; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0h
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 65536;
+    const uint32_t idesc = make_idesc(128, n, a_mn, b_mn);
+    const uint64_t lay = (uint64_t)(swz & 7) << 61;
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll 1
+      for (int ks = 0; ks < 16; ++ks) {
+        // operand strides as the megakernel uses them (no swizzle) or the canonical SW128 ones
+        uint64_t da, db;
+        if (swz == 0) {
+          da = a_mn ? make_desc(sa + ks * 256, 128, 4096) : make_desc(sa + ks * 4096, 128, 256);
+          db = b_mn ? make_desc(sb + ks * 256, 128, 4096 * (n > 128 ? 1 : 1)) : make_desc(sb + ks * 4096, 128, 256);
+        } else {
+          da = make_desc(sa + ks * 32, 16, 1024) | lay;
+          db = make_desc(sb + ks * 32, 16, 1024) | lay;
+        }
+        if (swz < 8) {
+          mma_f16(tmem + (ks & 1) * 256, da, db, idesc, 1);
+        } else {
+          // megakernel issue pattern: wide (N=256) + narrow (N=128) MMA per chunk, commit per chunk
+          const int pat = swz - 8;
+          mma_f16(tmem + (ks & 1) * 256, make_desc(sa + ks * 4096, 128, 256), make_desc(sb + ks * 256, 128, 4096),
+                  make_idesc(128, 256, 0, 1), 1);
+          mma_f16(tmem + (ks & 1) * 256, make_desc(sa + ks * 4096 + 2048, 128, 256), make_desc(sb + ks * 256, 128, 4096),
+                  (pat & 1) ? make_idesc(128, 256, 0, 1) : make_idesc(128, 128, 0, 1), 1);
+          if (pat & 2) mma_commit(&bar2);
+        }
+      }
+    }
+    mma_commit(&bar);
+    long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (blockIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  __syncthreads();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -735,6 +980,7 @@ static int32_t tc_ensure(neddf_field* f) {
     st.aux_ksteps = aux_pad / 16;
     st.h_ksteps = h_k / 16;
     st.bias_off = l * kWidth;
+    st.post = 0;
     S->pack.k_in[l] = f->shape_in[l];
     S->pack.aux_real[l] = aux_real;
     S->pack.aux_pad[l] = aux_pad;
@@ -743,17 +989,36 @@ static int32_t tc_ensure(neddf_field* f) {
     chunk += 2 * S->pack.ksteps[l];
     if (l == f->n_ddf - 1) {  // distance / aux heads after the trunk
       tc::Step& hs = S->step[si++];
-      hs.kind = tc::kStepHeadDA; hs.aux_ksteps = 0; hs.h_ksteps = kWidth / 16; hs.bias_off = 0;
+      hs.kind = tc::kStepHeadDA; hs.aux_ksteps = 0; hs.h_ksteps = kWidth / 16; hs.bias_off = 0; hs.post = 0;
       S->pack.chunk0[n_hidden] = chunk;
       chunk += 2;
     }
   }
   tc::Step& cs = S->step[si++];
-  cs.kind = tc::kStepHeadCol; cs.aux_ksteps = 0; cs.h_ksteps = kWidth / 16; cs.bias_off = 0;
+  cs.kind = tc::kStepHeadCol; cs.aux_ksteps = 0; cs.h_ksteps = kWidth / 16; cs.bias_off = 0; cs.post = 0;
   S->pack.chunk0[n_hidden + 1] = chunk;
   chunk += 2;
   S->n_steps = si;
   S->chunks_per_tile = chunk;
+  {
+    // AUX holds E_s until the last trunk layer that reads it (layer 0 or the last skip consumer);
+    // after that layer's epilogue the colour inputs E0|D can be written while later trunk layers
+    // run.  If that layer is the last trunk layer the heads step does it inline.
+    int last_aux = 0, head_da = -1, first_col = -1;
+    for (int i = 0; i < si; ++i) {
+      if (S->step[i].kind == tc::kStepHeadDA) head_da = i;
+      if (head_da < 0 && S->step[i].kind == tc::kStepHidden && S->step[i].aux_ksteps > 0) last_aux = i;
+      if (head_da >= 0 && first_col < 0 && S->step[i].kind == tc::kStepHidden) first_col = i;
+    }
+    if (last_aux + 1 < head_da) S->step[last_aux].post = 1;
+    else S->step[head_da].post = 1;
+    // after the first colour layer's epilogue AUX is dead again: next tile's prologue goes there
+    S->step[first_col].post = 2;
+  }
+  if (const char* e = std::getenv("NEDDF_TC_CLUSTER")) {
+    int c = std::atoi(e);
+    if (c == 1 || c == 2 || c == 4) S->cluster = c;
+  }
   if (cudaMalloc(&S->d_w, (size_t)chunk * tc::kStageBytes) != cudaSuccess ||
       cudaMalloc(&S->d_bias, (size_t)n_hidden * kWidth * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess) {
@@ -804,11 +1069,33 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
   P.w_tc = S->d_w;
   P.bias = S->d_bias;
   P.status = S->d_status;
+  P.timeline = S->timeline;
+  P.timeline_cap = S->timeline_cap;
   int64_t n_tiles = (p.n + tc::kTileS - 1) / tc::kTileS;
-  int grid = (int)std::min<int64_t>(n_tiles, sm_count());
+  int cluster = S->cluster;
+  int grid = (int)std::min<int64_t>((n_tiles + cluster - 1) / cluster * cluster, sm_count() / cluster * cluster);
+  if (n_tiles < 2 * cluster) {  // tiny launches: no point in pairing CTAs
+    cluster = 1;
+    grid = (int)std::min<int64_t>(n_tiles, sm_count());
+  }
+  P.cluster = cluster;
+  P.debug = 0;
+  if (const char* e = std::getenv("NEDDF_TC_DEBUG")) P.debug = std::atoi(e);
   auto launch = [&](auto kern) -> int32_t {
     NEDDF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-    kern<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(P);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = tc::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NEDDF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, P));
     NEDDF_LAUNCH_CHECK();
     return NEDDF_OK;
   };
@@ -818,6 +1105,15 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
     case NEDDF_ACT_LEAKYRELU: return launch(tc::field_tc_kernel<NEDDF_ACT_LEAKYRELU>);
   }
   return fail(NEDDF_E_INVALID, "tensor-core engine: unknown activation");
+}
+
+int32_t tc_set_timeline(neddf_field* f, long long* d_buf, int cap) {
+  int32_t rc = tc_ensure(f);
+  if (rc != NEDDF_OK) return rc;
+  tc::TcStorage* S = static_cast<tc::TcStorage*>(f->tc);
+  S->timeline = d_buf;
+  S->timeline_cap = d_buf ? cap : 0;
+  return NEDDF_OK;
 }
 
 int32_t tc_read_status(const neddf_field* f, int* out, cudaStream_t s) {
@@ -831,6 +1127,20 @@ int32_t tc_read_status(const neddf_field* f, int* out, cudaStream_t s) {
 }
 
 }  // namespace neddf
+
+extern "C" int32_t neddf_tc_mma_bench(int32_t a_mn, int32_t b_mn, int32_t swizzle, int32_t n, int32_t reps,
+                                      int64_t* d_cycles, void* stream) {
+  using namespace neddf;
+  if (!d_cycles || reps < 1 || n < 16 || n > 256 || (n % 16)) return fail(NEDDF_E_INVALID, "neddf_tc_mma_bench: bad arguments");
+  size_t smem = 196608;
+  NEDDF_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = 1;
+  if (const char* e = std::getenv("NEDDF_MMA_BENCH_GRID")) grid = std::max(1, std::atoi(e));
+  tc::tc_mma_bench_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a_mn, b_mn, swizzle, n, reps,
+                                                                 reinterpret_cast<long long*>(d_cycles));
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}
 
 extern "C" int32_t neddf_tc_selftest(const float* d_a, const float* d_b, int32_t m, int32_t n, int32_t k, float* d_c,
                                      void* stream) {
