@@ -203,6 +203,12 @@ int64_t neddf_launch_count(void);
 int32_t neddf_tc_selftest(const float* d_a, const float* d_b, int32_t m, int32_t n, int32_t k,
                           float* d_c, void* stream);
 
+/* Self-test of the "A operand in tensor memory" MMA form (weights written to TMEM with
+ * tcgen05.st, activations MN-major in shared memory): C[128,128] = A[128,k] B[128,k]^T, averaged
+ * over `reps` repeated accumulations; d_cycles[0] (optional) = SM cycles for reps*k/16*3 MMAs. */
+int32_t neddf_tc_selftest_ts(const float* d_a, const float* d_b, int32_t k, float* d_c, int64_t* d_cycles,
+                             int32_t reps, void* stream);
+
 /* tcgen05 issue-rate microbenchmark (profiling aid): reps x 16 MMAs 128 x n x 16 on resident
  * shared-memory operands; a_mn / b_mn = 1 for MN-major operands, swizzle 0 (none) or 2 (128B).
  * d_cycles[0] = SM cycles to issue, d_cycles[1] = cycles until the last MMA completed. */

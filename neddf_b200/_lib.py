@@ -64,6 +64,7 @@ _SIGNATURES = {
     "neddf_sample_pdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "neddf_invert_cdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "neddf_tc_mma_bench": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "neddf_tc_selftest_ts": (_I32, [_P, _P, _I32, _P, _P, _I32, _P]),
     "neddf_tc_selftest": (_I32, [_P, _P, _I32, _I32, _I32, _P, _P]),
 }
 

@@ -70,8 +70,8 @@ struct Scratch {
   HeadOut head[kTileS];
   uint64_t full[kNumStages];
   uint64_t empty[kNumStages];
-  uint64_t act_ready;
-  uint64_t acc_ready;
+  uint64_t act_ready[2];  // epilogue group h -> MMA: accumulator h drained, H[k-half h] rewritten
+  uint64_t acc_ready[2];  // MMA -> epilogue group h: accumulator h complete
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -216,6 +216,27 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory ("TS"): A[m][k] lives in lane m, 32-bit column k/2 (two fp16 per
+// column, even k in the low half) - cute::UMMA::tmem_frg_1sm<half_t>.
+__device__ __forceinline__ void mma_f16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Warp-uniform variants: the whole warp executes them with identical operands and one elected
 // lane issues.  Keeping the issuing code convergent lets ptxas hold descriptors in uniform
 // registers; under `if (lane == 0)` it wraps every UTCHMMA in an ELECT/R2UR.BROADCAST loop.
@@ -442,8 +463,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
       mbar_init(&sc->full[i], 1);
       mbar_init(&sc->empty[i], CL);  // one tcgen05.commit arrival from every CTA of the cluster
     }
-    mbar_init(&sc->act_ready, kEpiThreads);
-    mbar_init(&sc->acc_ready, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&sc->act_ready[h], kEpiThreads / 2);
+      mbar_init(&sc->acc_ready[h], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps + 1) tmem_alloc(&sc->tmem_base, kTmemCols);
@@ -495,11 +518,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     for (int64_t t = 0; t < my_tiles; ++t) {
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.step[si];
-        mbar_wait(&sc->act_ready, act_phase);
-        act_phase ^= 1;
-        tc_fence_after();
         const int tl = (int)(t * P.n_steps + si);
         const bool stamp = P.timeline && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
+        // act_ready[h] of the previous step: epilogue group h has drained accumulator h and
+        // rewritten H[k-half h].  The first layer of a tile reads AUX written by both groups.
+        mbar_wait(&sc->act_ready[0], act_phase);
+        if (st.kind != kStepHidden || si == 0) mbar_wait(&sc->act_ready[1], act_phase);
+        tc_fence_after();
         if (stamp) P.timeline[6 * tl + 0] = clock64();
         if (st.kind == kStepHidden) {
           // Per K-step and channel half one 8 KB chunk [A_hi | A_lo] and two MMAs:
@@ -507,25 +532,33 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           // (B = [hi rows | lo rows] as one N = 256 operand).  tcgen05.mma issue is not free -
           // every instruction between two MMAs lengthens the phase (tools/mma_bench.py) - so ring
           // positions are counters (no 64-bit div/mod) and descriptors advance by one add.
-          const int ksteps = st.aux_ksteps + st.h_ksteps;
-          uint64_t db = make_desc(st.aux_ksteps ? s_ahi : s_hhi, 128, st.aux_ksteps ? kAuxK * 16 : kHK * 16);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            if (ks == st.aux_ksteps && ks > 0) db = make_desc(s_hhi, 128, kHK * 16);
-            const uint32_t acc = ks > 0;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+          // Issue order (half 0, G0), (half 1, G0), (half 0, G1), (half 1, G1) - see chunk_pos().
+          const int nA = st.aux_ksteps, n1 = st.h_ksteps / 2, n0 = nA + st.h_ksteps - n1;
+          const uint64_t db_aux = make_desc(s_ahi, 128, kAuxK * 16), db_h = make_desc(s_hhi, 128, kHK * 16);
+          auto issue = [&](int half, int ks_begin, int ks_end) {
+            const uint32_t d = tmem + half * (2 * kRows);
+            for (int ks = ks_begin; ks < ks_end; ++ks) {
+              const uint64_t db = (ks < nA) ? db_aux + (uint64_t)(ks * 16) : db_h + (uint64_t)((ks - nA) * 16);
               if (!(P.debug & 1)) mbar_wait(&sc->full[stage], full_par);
               tc_fence_after();
               const uint64_t a = da0 + (uint64_t)(stage * (kStageBytes >> 4));
-              const uint32_t d = tmem + half * (2 * kRows);
-              mma_f16_elect(d, a, db, kIdescHiddenWide, acc);
+              mma_f16_elect(d, a, db, kIdescHiddenWide, ks > 0);
               mma_f16_elect(d, a + (4096 >> 4), db, kIdescHidden, 1);
               if (CL == 1) mma_commit_elect(&sc->empty[stage]);
               else mma_commit_mc_elect(&sc->empty[stage], cmask);
               advance();
             }
-            db += 256 >> 4;  // next K-step: 16 k x 16 bytes
+          };
+          issue(0, 0, n0);
+          if (si != 0) {  // accumulator 1 free, H[k >= 128] ready
+            mbar_wait(&sc->act_ready[1], act_phase);
+            tc_fence_after();
           }
+          issue(1, 0, n0);
+          issue(0, n0, n0 + n1);
+          mma_commit_elect(&sc->acc_ready[0]);
+          issue(1, n0, n0 + n1);
+          mma_commit_elect(&sc->acc_ready[1]);
         } else {
           // heads: D[row, n] = sum_k H[row,k] * Wh[n,k]; two chunks: hi then lo head weights
           const int st0 = stage;
@@ -556,8 +589,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             mma_commit_mc_elect(&sc->empty[st0], cmask);
             mma_commit_mc_elect(&sc->empty[st1], cmask);
           }
+          mma_commit_elect(&sc->acc_ready[0]);
+          mma_commit_elect(&sc->acc_ready[1]);
         }
-        mma_commit_elect(&sc->acc_ready);
+        act_phase ^= 1;
         if (stamp) P.timeline[6 * tl + 1] = clock64();
       }
     }
@@ -599,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     if (my_tiles > 0) {
       prologue(cid * CL + crank);
       fence_async_smem();
-      mbar_arrive(&sc->act_ready);
+      mbar_arrive(&sc->act_ready[half]);
     }
 
     for (int64_t t = 0; t < my_tiles; ++t) {
@@ -609,8 +644,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         const Step& st = P.step[si];
         // one thread polls the mbarrier; the other 511 sleep in a hardware named barrier instead of
         // spinning on shared memory while the tensor core is streaming operands from it
-        if (tid == 0) mbar_wait(&sc->acc_ready, acc_phase);
-        asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+        if ((tid & 127) == 0 && (warp & 3) == 0 && (warp >> 3) == 0) mbar_wait(&sc->acc_ready[half], acc_phase);
+        if (half == 0) asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads / 2) : "memory");
+        else asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads / 2) : "memory");
         acc_phase ^= 1;
         tc_fence_after();
         const int tl = (int)(t * P.n_steps + si);
@@ -701,7 +737,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         tc_fence_before();
         fence_async_smem();
         if (stamp) P.timeline[6 * tl + 3] = clock64();
-        if (t + 1 < my_tiles || si + 1 < P.n_steps) mbar_arrive(&sc->act_ready);
+        if (t + 1 < my_tiles || si + 1 < P.n_steps) mbar_arrive(&sc->act_ready[half]);
         // work that only feeds later steps runs here, under the next step's MMA phase; its
         // shared-memory writes are published by the fence + arrive of the following steps
         if (st.kind == kStepHidden && st.post == 1) colour_prep();
@@ -731,6 +767,15 @@ struct TcPackArgs {
   int n_hidden;
 };
 
+// Consumption order of a hidden layer's chunks.  K-steps split into G0 = [AUX steps + first half
+// of the H steps] and G1 = [second half of the H steps]; the MMA warp issues
+// (half 0, G0), (half 1, G0), (half 0, G1), (half 1, G1) so that channel half 0 completes a quarter
+// layer before half 1 and the two epilogue groups can trail the tensor core (see the kernel).
+__host__ __device__ __forceinline__ int chunk_pos(int ksteps, int aux_ksteps, int ks, int half) {
+  const int n1 = (ksteps - aux_ksteps) / 2, n0 = ksteps - n1;
+  return (ks < n0) ? half * n0 + ks : 2 * n0 + half * n1 + (ks - n0);
+}
+
 __global__ void tc_pack_hidden_kernel(TcPackArgs a, unsigned char* __restrict__ dst, float* __restrict__ bias) {
   const int l = blockIdx.y;
   const int total = a.ksteps[l] * 2 * 128 * 16;  // (kstep, half, m, k)
@@ -744,7 +789,7 @@ __global__ void tc_pack_hidden_kernel(TcPackArgs a, unsigned char* __restrict__ 
     float w = (row >= 0) ? a.w[l][(size_t)row * kWidth + 128 * half + m] : 0.f;
     __half hi = __float2half_rn(w);
     __half lo = __float2half_rn(w - __half2float(hi));
-    unsigned char* chunk = dst + (size_t)(a.chunk0[l] + ks * 2 + half) * kStageBytes;
+    unsigned char* chunk = dst + (size_t)(a.chunk0[l] + chunk_pos(a.ksteps[l], a.aux_pad[l] / 16, ks, half)) * kStageBytes;
     *reinterpret_cast<__half*>(chunk + wchunk_off(m, k)) = hi;
     *reinterpret_cast<__half*>(chunk + 4096 + wchunk_off(m, k)) = lo;
   }
@@ -871,6 +916,83 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// TS-mode self-test: C[m, n] = sum_k A[m,k] B[n,k] with A (weights) written to tensor memory by
+// tcgen05.st and B (activations, MN-major) in shared memory; m = n = 128.
+__global__ void __launch_bounds__(128, 1) tc_selftest_ts_kernel(const float* __restrict__ A,
+                                                                const float* __restrict__ B, int k,
+                                                                float* __restrict__ C, long long* __restrict__ cyc,
+                                                                int reps) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* h_hi = smem;
+  unsigned char* h_lo = smem + kHBytes;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < 128 * k; idx += 128) {
+    int kk = idx % k, r = idx / k;
+    float b = B[(size_t)r * k + kk];
+    __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
+    *reinterpret_cast<__half*>(h_hi + act_off(r, kk, kHK)) = hi;
+    *reinterpret_cast<__half*>(h_lo + act_off(r, kk, kHK)) = lo;
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  // A: lane = row m; per K-step 8 columns hi at 256 + ks*16, 8 columns lo right after
+  const int m = 32 * warp + lane;
+  for (int ks = 0; ks < k / 16; ++ks) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a0 = A[(size_t)m * k + ks * 16 + 2 * j], a1 = A[(size_t)m * k + ks * 16 + 2 * j + 1];
+      float amax = 0.f;
+      split2(a0, a1, hi[j], lo[j], amax);
+    }
+    const uint32_t ta = tmem + ((uint32_t)(32 * warp) << 16) + 256 + ks * 16;
+    tmem_st8(ta, hi);
+    tmem_st8(ta + 8, lo);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    const uint32_t s_hhi = smem_u32(h_hi), s_hlo = smem_u32(h_lo);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int ks = 0; ks < k / 16; ++ks) {
+        const uint64_t db_hi = make_desc(s_hhi + ks * 256, 128, kHK * 16), db_lo = make_desc(s_hlo + ks * 256, 128, kHK * 16);
+        const uint32_t ta = tmem + 256 + ks * 16;
+        mma_f16_ts_elect(tmem, ta, db_hi, kIdescHidden, (r | ks) > 0);
+        mma_f16_ts_elect(tmem, ta + 8, db_hi, kIdescHidden, 1);
+        mma_f16_ts_elect(tmem, ta, db_lo, kIdescHidden, 1);
+      }
+    }
+    mma_commit_elect(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (lane == 0 && cyc) cyc[0] = t1 - t0;
+  }
+  __syncthreads();
+  tc_fence_after();
+  for (int cb = 0; cb < 128 / 16; ++cb) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + cb * 16, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) C[(size_t)m * 128 + cb * 16 + i] = v[i] / (float)reps;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1138,6 +1260,18 @@ extern "C" int32_t neddf_tc_mma_bench(int32_t a_mn, int32_t b_mn, int32_t swizzl
   if (const char* e = std::getenv("NEDDF_MMA_BENCH_GRID")) grid = std::max(1, std::atoi(e));
   tc::tc_mma_bench_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a_mn, b_mn, swizzle, n, reps,
                                                                  reinterpret_cast<long long*>(d_cycles));
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}
+
+extern "C" int32_t neddf_tc_selftest_ts(const float* d_a, const float* d_b, int32_t k, float* d_c, int64_t* d_cycles,
+                                        int32_t reps, void* stream) {
+  using namespace neddf;
+  if (k < 16 || k > 256 || (k % 16) != 0 || reps < 1) return fail(NEDDF_E_INVALID, "neddf_tc_selftest_ts: bad k / reps");
+  if (!d_a || !d_b || !d_c) return fail(NEDDF_E_INVALID, "neddf_tc_selftest_ts: NULL pointer");
+  size_t smem = 2 * tc::kHBytes;
+  NEDDF_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::tc_selftest_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_a, d_b, k, d_c, reinterpret_cast<long long*>(d_cycles), reps);
   NEDDF_LAUNCH_CHECK();
   return NEDDF_OK;
 }
