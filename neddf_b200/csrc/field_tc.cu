@@ -47,11 +47,15 @@ constexpr int kTileS = 32;              // samples per tile
 constexpr int kRows = 4 * kTileS;       // 128 = MMA N (hidden) / M (heads)
 constexpr int kHK = 256;                // K capacity of H
 constexpr int kAuxK = 96;               // K capacity of AUX
-constexpr int kStageBytes = 8192;
-constexpr int kNumStages = 5;
+constexpr int kChunkBytes = 8192;   // one weight chunk: 128 rows x (8 words hi | 8 words lo)
+constexpr int kStageBytes = kChunkBytes;
+constexpr int kARing = 16;          // weight chunks resident in tensor memory (16 columns each)
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = kEpiThreads + 64;
+constexpr int kMmaWarp = kEpiWarps;          // warp 16
+constexpr int kLoadWarps = 8;                // warps 17-24: lane quarter w%4, chunk parity (w-17)/4
+constexpr int kThreads = kEpiThreads + 32 + kLoadWarps * 32;
+constexpr uint32_t kACol = 256;              // first TMEM column of the weight ring
 constexpr int kMaxSteps = kMaxHidden + 2;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kHeadCol = 0;  // head results alias the (then idle) hidden accumulators
@@ -62,14 +66,14 @@ constexpr uint32_t kOffHHi = 0;
 constexpr uint32_t kOffHLo = kOffHHi + kHBytes;
 constexpr uint32_t kOffAuxHi = kOffHLo + kHBytes;
 constexpr uint32_t kOffAuxLo = kOffAuxHi + kAuxBytes;
-constexpr uint32_t kOffStages = kOffAuxLo + kAuxBytes;
-constexpr uint32_t kOffScratch = kOffStages + kNumStages * kStageBytes;
+constexpr uint32_t kOffHeadW = kOffAuxLo + kAuxBytes;       // (ddf,aux) hi | lo | colour hi | lo
+constexpr uint32_t kOffScratch = kOffHeadW + 4 * kChunkBytes;
 
 struct Scratch {
   float geo[kTileS][12];   // pos[3], dir[3], var[3], pad
   HeadOut head[kTileS];
-  uint64_t full[kNumStages];
-  uint64_t empty[kNumStages];
+  uint64_t a_full[kARing];   // loaders -> MMA: chunk written to tensor memory
+  uint64_t a_empty[kARing];  // MMA -> loaders: chunk consumed
   uint64_t act_ready[2];  // epilogue group h -> MMA: accumulator h drained, H[k-half h] rewritten
   uint64_t acc_ready[2];  // MMA -> epilogue group h: accumulator h complete
   uint32_t tmem_base;
@@ -99,8 +103,6 @@ struct TcParams {
   const unsigned char* w_tc;  // packed chunks, kStageBytes each, in consumption order
   const float* bias;          // [n_hidden][256] plain channel order
   int* status;
-  int debug;            // profiling experiments: bit0 = no weight refills (results invalid)
-  int cluster;          // CTAs per cluster sharing one multicast weight stream (1, 2 or 4)
   long long* timeline;  // optional: CTA 0 writes 6 values per step (profiling aid)
   int timeline_cap;
 };
@@ -437,31 +439,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
   unsigned char* h_lo = smem + kOffHLo;
   unsigned char* aux_hi = smem + kOffAuxHi;
   unsigned char* aux_lo = smem + kOffAuxLo;
-  unsigned char* stages = smem + kOffStages;
+  unsigned char* head_w = smem + kOffHeadW;
   Scratch* sc = reinterpret_cast<Scratch*>(smem + kOffScratch);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
-  // Tiles are handed out in groups of `cluster` consecutive tiles, one group per cluster per
-  // round, so that all CTAs of a cluster run the same number of tiles (they share one multicast
-  // weight stream and must consume it in lockstep).  A CTA whose tile index is past the end
-  // computes a dummy tile (no valid samples, nothing written).
-  const int CL = P.cluster;
-  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   const int64_t n_tiles = (p.n + kTileS - 1) / kTileS;
-  const int64_t n_groups = (n_tiles + CL - 1) / CL;
-  const int64_t cid = blockIdx.x / CL, n_clusters = gridDim.x / CL;
   int64_t my_tiles = 0;
-  if (cid < n_groups) my_tiles = (n_groups - 1 - cid) / n_clusters + 1;
+  if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - blockIdx.x) / gridDim.x + 1;
   const int64_t total_chunks = my_tiles * P.chunks_per_tile;
-  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   if (tid == 0) {
-    for (int i = 0; i < kNumStages; ++i) {
-      mbar_init(&sc->full[i], 1);
-      mbar_init(&sc->empty[i], CL);  // one tcgen05.commit arrival from every CTA of the cluster
+    for (int i = 0; i < kARing; ++i) {
+      mbar_init(&sc->a_full[i], 4);           // one arrival per lane quarter (4 loader warps per chunk)
+      mbar_init(&sc->a_empty[i], 1);          // tcgen05.commit
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&sc->act_ready[h], kEpiThreads / 2);
@@ -469,52 +462,89 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kEpiWarps + 1) tmem_alloc(&sc->tmem_base, kTmemCols);
+  // head weights (B operands of the standard-orientation head MMAs) stay resident: 4 x 8 KB
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.w_tc + (size_t)P.chunks_per_tile * kChunkBytes);
+    uint4* dst = reinterpret_cast<uint4*>(head_w);
+    for (int i = tid; i < 4 * kChunkBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  if (warp == kMmaWarp) tmem_alloc(&sc->tmem_base, kTmemCols);
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = sc->tmem_base;
 
-  if (warp == kEpiWarps) {
-    // ===================== TMA producer =====================================================
-    if (lane == 0 && !(P.debug & 1)) {
-      int stage = 0, cidx = 0;
-      uint32_t par = 0;  // parity of the previous use's phase of empty[]; the first pass does not wait
-      bool first_pass = true;
-      for (int64_t g = 0; g < total_chunks; ++g) {
-        if (!first_pass) mbar_wait(&sc->empty[stage], par);
-        mbar_expect_tx(&sc->full[stage], kStageBytes);
-        const unsigned char* src = P.w_tc + (size_t)cidx * kStageBytes;
-        if (CL == 1) {
-          bulk_g2s(stages + stage * kStageBytes, src, kStageBytes, &sc->full[stage]);
-        } else if ((uint32_t)(cidx % CL) == crank) {
-          // this CTA fetches the chunk for the whole cluster: one L2 read, CL shared-memory copies
-          // (chunks_per_tile is even, so cidx % CL == g % CL for CL in {2,4} when it divides it)
-          bulk_g2s_mc(stages + stage * kStageBytes, src, kStageBytes, &sc->full[stage], cmask);
-        }
-        if (++cidx == P.chunks_per_tile) cidx = 0;
-        if (++stage == kNumStages) {
-          stage = 0;
-          if (first_pass) first_pass = false;
-          else par ^= 1;
+  if (warp > kMmaWarp) {
+    // ===================== weight loaders: L2 -> registers -> tensor memory ======================
+    // Chunk (K-step, channel half) = 128 rows x [8 words hi | 8 words lo] (two fp16 per word).
+    // Lane = row of this warp's TMEM lane quarter; 64 contiguous bytes per lane, 2 KB per warp.
+    // Eight warps: two per lane quarter, taking alternate chunks, so that more loads are in
+    // flight than the L2 latency x 42 B/clk the tensor core consumes.
+    const int quarter = warp & 3;
+    const int cpar = (warp - kMmaWarp - 1) >> 2;  // this warp loads chunks g with (g & 1) == cpar
+    const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
+    const uint4* base = reinterpret_cast<const uint4*>(P.w_tc) + (size_t)(32 * quarter + lane) * 4;
+    constexpr int kDepth = 3;  // own chunks in flight in registers (= 6 chunks ahead of the MMA warp)
+    uint4 r[kDepth][4];
+    auto fetch = [&](int slot, int chunk) {
+      const uint4* src = base + (size_t)chunk * (kChunkBytes / 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[slot][j] = __ldg(src + j);
+    };
+    // chunks_per_tile is even, so the within-tile index of chunk g has the parity of g
+    int fidx = cpar;  // within-tile index of the next chunk to fetch
+    int64_t gf = cpar;
+#pragma unroll
+    for (int i = 0; i < kDepth; ++i) {
+      if (gf < total_chunks) {
+        fetch(i, fidx);
+        fidx += 2;
+        if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
+        gf += 2;
+      }
+    }
+    int stage = cpar;
+    uint32_t par = 0;
+    bool first_pass = true;
+    int64_t g = cpar;
+    while (g < total_chunks) {
+#pragma unroll
+      for (int i = 0; i < kDepth; ++i) {
+        if (g < total_chunks) {
+          if (!first_pass) mbar_wait(&sc->a_empty[stage], par);
+          tc_fence_after();
+          const uint32_t ta = tmem + lane_addr + kACol + stage * 16;
+          const uint32_t w0[8] = {r[i][0].x, r[i][0].y, r[i][0].z, r[i][0].w, r[i][1].x, r[i][1].y, r[i][1].z, r[i][1].w};
+          const uint32_t w1[8] = {r[i][2].x, r[i][2].y, r[i][2].z, r[i][2].w, r[i][3].x, r[i][3].y, r[i][3].z, r[i][3].w};
+          tmem_st8(ta, w0);
+          tmem_st8(ta + 8, w1);
+          if (gf < total_chunks) {  // refill this register slot (the scoreboard orders it after the stores read it)
+            fetch(i, fidx);
+            fidx += 2;
+            if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
+            gf += 2;
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&sc->a_full[stage]);
+          g += 2;
+          stage += 2;
+          if (stage >= kARing) {
+            stage -= kARing;
+            if (first_pass) first_pass = false;
+            else par ^= 1;
+          }
         }
       }
     }
-  } else if (warp == kEpiWarps + 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (whole warp, one elected lane issues) ===================
-    const uint32_t s_hhi = smem_u32(h_hi), s_ahi = smem_u32(aux_hi), s_hlo = smem_u32(h_lo);
-    const uint32_t s_stage = smem_u32(stages);
-    const uint64_t da0 = make_desc(s_stage, 128, 256);
+    const uint32_t s_hhi = smem_u32(h_hi), s_ahi = smem_u32(aux_hi), s_hlo = smem_u32(h_lo), s_alo = smem_u32(aux_lo);
+    const uint32_t s_head = smem_u32(head_w);
     int stage = 0;          // ring position of the next chunk
-    uint32_t full_par = 0;  // parity to wait for on full[stage]
+    uint32_t full_par = 0;  // parity to wait for on a_full[stage]
     uint32_t act_phase = 0;
-    auto advance = [&]() {
-      if (++stage == kNumStages) {
-        stage = 0;
-        full_par ^= 1;
-      }
-    };
     for (int64_t t = 0; t < my_tiles; ++t) {
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.step[si];
@@ -525,28 +555,35 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         mbar_wait(&sc->act_ready[0], act_phase);
         if (st.kind != kStepHidden || si == 0) mbar_wait(&sc->act_ready[1], act_phase);
         tc_fence_after();
+        long long waited = 0;
         if (stamp) P.timeline[6 * tl + 0] = clock64();
         if (st.kind == kStepHidden) {
-          // Per K-step and channel half one 8 KB chunk [A_hi | A_lo] and two MMAs:
-          //   cols [0,128)   += A_hi*B_hi + A_lo*B_hi,   cols [128,256) += A_hi*B_lo
-          // (B = [hi rows | lo rows] as one N = 256 operand).  tcgen05.mma issue is not free -
-          // every instruction between two MMAs lengthens the phase (tools/mma_bench.py) - so ring
-          // positions are counters (no 64-bit div/mod) and descriptors advance by one add.
-          // Issue order (half 0, G0), (half 1, G0), (half 0, G1), (half 1, G1) - see chunk_pos().
+          // Per (K-step, channel half) one weight chunk in tensor memory and three MMAs
+          //   D_half += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (A from TMEM: 64 cycles each)
+          // Issue order (half 0, G0), (half 1, G0), (half 0, G1), (half 1, G1) - see chunk_pos():
+          // half 0 completes a quarter layer early, so the two epilogue groups trail the tensor
+          // core instead of alternating with it.
           const int nA = st.aux_ksteps, n1 = st.h_ksteps / 2, n0 = nA + st.h_ksteps - n1;
-          const uint64_t db_aux = make_desc(s_ahi, 128, kAuxK * 16), db_h = make_desc(s_hhi, 128, kHK * 16);
+          const uint64_t dba_hi = make_desc(s_ahi, 128, kAuxK * 16), dba_lo = make_desc(s_alo, 128, kAuxK * 16);
+          const uint64_t dbh_hi = make_desc(s_hhi, 128, kHK * 16), dbh_lo = make_desc(s_hlo, 128, kHK * 16);
           auto issue = [&](int half, int ks_begin, int ks_end) {
-            const uint32_t d = tmem + half * (2 * kRows);
+            const uint32_t d = tmem + half * kRows;
             for (int ks = ks_begin; ks < ks_end; ++ks) {
-              const uint64_t db = (ks < nA) ? db_aux + (uint64_t)(ks * 16) : db_h + (uint64_t)((ks - nA) * 16);
-              if (!(P.debug & 1)) mbar_wait(&sc->full[stage], full_par);
+              const uint64_t off = (ks < nA) ? (uint64_t)(ks * 16) : (uint64_t)((ks - nA) * 16);
+              const uint64_t db_hi = ((ks < nA) ? dba_hi : dbh_hi) + off, db_lo = ((ks < nA) ? dba_lo : dbh_lo) + off;
+              const long long w0 = stamp ? clock64() : 0;
+              mbar_wait(&sc->a_full[stage], full_par);
+              if (stamp) waited += clock64() - w0;
               tc_fence_after();
-              const uint64_t a = da0 + (uint64_t)(stage * (kStageBytes >> 4));
-              mma_f16_elect(d, a, db, kIdescHiddenWide, ks > 0);
-              mma_f16_elect(d, a + (4096 >> 4), db, kIdescHidden, 1);
-              if (CL == 1) mma_commit_elect(&sc->empty[stage]);
-              else mma_commit_mc_elect(&sc->empty[stage], cmask);
-              advance();
+              const uint32_t a = tmem + kACol + stage * 16;
+              mma_f16_ts_elect(d, a, db_hi, kIdescHidden, ks > 0);
+              mma_f16_ts_elect(d, a + 8, db_hi, kIdescHidden, 1);
+              mma_f16_ts_elect(d, a, db_lo, kIdescHidden, 1);
+              mma_commit_elect(&sc->a_empty[stage]);
+              if (++stage == kARing) {
+                stage = 0;
+                full_par ^= 1;
+              }
             }
           };
           issue(0, 0, n0);
@@ -560,53 +597,37 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           issue(1, n0, n0 + n1);
           mma_commit_elect(&sc->acc_ready[1]);
         } else {
-          // heads: D[row, n] = sum_k H[row,k] * Wh[n,k]; two chunks: hi then lo head weights
-          const int st0 = stage;
-          const uint32_t p0 = full_par;
-          advance();
-          const int st1 = stage;
-          const uint32_t p1 = full_par;
-          advance();
-          if (!(P.debug & 1)) {
-            mbar_wait(&sc->full[st0], p0);
-            mbar_wait(&sc->full[st1], p1);
-          }
-          tc_fence_after();
-          const uint32_t w_hi = s_stage + st0 * kStageBytes, w_lo = s_stage + st1 * kStageBytes;
+          // heads (standard orientation): D[row, n] = sum_k H[row,k] * Wh[n,k], weights resident
+          const uint32_t w = s_head + (st.kind == kStepHeadDA ? 0 : 2 * kChunkBytes);
           const uint32_t d = tmem + kHeadCol;
           uint64_t da_hi = make_desc(s_hhi, 128, kHK * 16), da_lo = make_desc(s_hlo, 128, kHK * 16);
-          uint64_t db_hi = make_desc(w_hi, 128, 4096), db_lo = make_desc(w_lo, 128, 4096);
+          uint64_t db_hi = make_desc(w, 128, 4096), db_lo = make_desc(w + kChunkBytes, 128, 4096);
           for (int ks = 0; ks < kHK / 16; ++ks) {
             mma_f16_elect(d, da_hi, db_hi, kIdescHead, ks > 0);
             mma_f16_elect(d, da_lo, db_hi, kIdescHead, 1);
             mma_f16_elect(d, da_hi, db_lo, kIdescHead, 1);
             da_hi += 16; da_lo += 16; db_hi += 16; db_lo += 16;
           }
-          if (CL == 1) {
-            mma_commit_elect(&sc->empty[st0]);
-            mma_commit_elect(&sc->empty[st1]);
-          } else {
-            mma_commit_mc_elect(&sc->empty[st0], cmask);
-            mma_commit_mc_elect(&sc->empty[st1], cmask);
-          }
           mma_commit_elect(&sc->acc_ready[0]);
           mma_commit_elect(&sc->acc_ready[1]);
         }
         act_phase ^= 1;
-        if (stamp) P.timeline[6 * tl + 1] = clock64();
+        if (stamp) {
+          P.timeline[6 * tl + 1] = clock64();
+          P.timeline[6 * tl + 4] = waited;
+        }
       }
     }
   } else {
     // ===================== epilogue warps =====================================================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = (warp >> 2) & 1;    // accumulator half (channels 128*half ..)
+    const int half = (warp >> 2) & 1;    // accumulator half (channels 128*half ..) = epilogue group
     const int shalf = warp >> 3;         // which 16 samples (64 columns) of the tile this warp handles
     const int ch = 128 * half + 32 * quarter + lane;
     const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
     float bad = 0.f;  // max |operand value| seen (fp16 range check)
     uint32_t acc_phase = 0;
 
-    // prologue of the first tile
     auto prologue = [&](int64_t tile) {
       const int64_t n0 = tile * kTileS;
       if (tid < kTileS) tile_geometry(p, sc, n0, tid);
@@ -632,19 +653,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
     };
     if (my_tiles > 0) {
-      prologue(cid * CL + crank);
+      prologue(blockIdx.x);
       fence_async_smem();
       mbar_arrive(&sc->act_ready[half]);
     }
 
     for (int64_t t = 0; t < my_tiles; ++t) {
-      const int64_t tile = (cid + t * n_clusters) * CL + crank;
+      const int64_t tile = blockIdx.x + t * gridDim.x;
       const int64_t n0 = tile * kTileS;
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.step[si];
-        // one thread polls the mbarrier; the other 511 sleep in a hardware named barrier instead of
-        // spinning on shared memory while the tensor core is streaming operands from it
-        if ((tid & 127) == 0 && (warp & 3) == 0 && (warp >> 3) == 0) mbar_wait(&sc->acc_ready[half], acc_phase);
+        // one thread per group polls the mbarrier; the rest sleep in a hardware named barrier
+        if (lane == 0 && quarter == 0 && shalf == 0) mbar_wait(&sc->acc_ready[half], acc_phase);
         if (half == 0) asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads / 2) : "memory");
         else asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads / 2) : "memory");
         acc_phase ^= 1;
@@ -654,14 +674,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         if (stamp) P.timeline[6 * tl + 2] = clock64();
         if (st.kind == kStepHidden) {
           const float bias = __ldg(P.bias + st.bias_off + ch);
-          const uint32_t tbase = tmem + lane_addr + half * (2 * kRows);
+          const uint32_t tbase = tmem + lane_addr + half * kRows;
 #pragma unroll 1
           for (int cb = 4 * shalf; cb < 4 * shalf + 4; ++cb) {  // 16 columns = 4 samples per load
-            float v[16], v2[16];
+            float v[16];
             tmem_ld16(tbase + cb * 16, v);
-            tmem_ld16(tbase + kRows + cb * 16, v2);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += v2[i];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {  // 2 samples = one 16-byte row group
               float y0, d0, y1, d1;
@@ -702,7 +719,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           }
           if (st.post == 1) colour_prep();  // only when no earlier MMA phase could hide it
         } else {
-          // colour head (neddf.py:257) + penalties (:259-300) + outputs, then next tile's prologue
+          // colour head (neddf.py:257) + penalties (:259-300) + outputs
           if (warp < 4) {
             float v[4];
             tmem_ld4(tmem + lane_addr + kHeadCol, v);
@@ -741,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         // work that only feeds later steps runs here, under the next step's MMA phase; its
         // shared-memory writes are published by the fence + arrive of the following steps
         if (st.kind == kStepHidden && st.post == 1) colour_prep();
-        if (st.post == 2 && t + 1 < my_tiles) prologue(tile + n_clusters * CL);
+        if (st.post == 2 && t + 1 < my_tiles) prologue(tile + gridDim.x);
       }
     }
     if (!(bad < 65504.0f) && P.status) atomicOr(P.status, 4);
@@ -749,8 +766,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
-  if (warp == kEpiWarps + 1) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -789,9 +805,10 @@ __global__ void tc_pack_hidden_kernel(TcPackArgs a, unsigned char* __restrict__ 
     float w = (row >= 0) ? a.w[l][(size_t)row * kWidth + 128 * half + m] : 0.f;
     __half hi = __float2half_rn(w);
     __half lo = __float2half_rn(w - __half2float(hi));
-    unsigned char* chunk = dst + (size_t)(a.chunk0[l] + chunk_pos(a.ksteps[l], a.aux_pad[l] / 16, ks, half)) * kStageBytes;
-    *reinterpret_cast<__half*>(chunk + wchunk_off(m, k)) = hi;
-    *reinterpret_cast<__half*>(chunk + 4096 + wchunk_off(m, k)) = lo;
+    unsigned char* chunk = dst + (size_t)(a.chunk0[l] + chunk_pos(a.ksteps[l], a.aux_pad[l] / 16, ks, half)) * kChunkBytes;
+    // tensor-memory A layout: row m = lane, k pairs packed per 32-bit column; 8 hi words then 8 lo words
+    *reinterpret_cast<__half*>(chunk + m * 64 + k * 2) = hi;
+    *reinterpret_cast<__half*>(chunk + m * 64 + 32 + k * 2) = lo;
   }
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < kWidth; c += blockDim.x) bias[l * kWidth + c] = a.b[l][c];
@@ -823,11 +840,6 @@ struct TcStorage {
   TcPackArgs pack;
   long long* timeline = nullptr;
   int timeline_cap = 0;
-  // CTAs sharing one multicast weight stream.  Measured on B200: 1 -> 8.5k cycles per 256-K layer,
-  // 2 / 4 -> 11.9k / 11.6k (the lockstep coupling of the shared 5-stage ring costs more than the L2
-  // traffic it saves; the weight stream is not the bottleneck), so the default is 1.
-  // NEDDF_TC_CLUSTER=1|2|4 overrides.
-  int cluster = 1;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1112,14 +1124,14 @@ static int32_t tc_ensure(neddf_field* f) {
     if (l == f->n_ddf - 1) {  // distance / aux heads after the trunk
       tc::Step& hs = S->step[si++];
       hs.kind = tc::kStepHeadDA; hs.aux_ksteps = 0; hs.h_ksteps = kWidth / 16; hs.bias_off = 0; hs.post = 0;
-      S->pack.chunk0[n_hidden] = chunk;
-      chunk += 2;
     }
   }
   tc::Step& cs = S->step[si++];
   cs.kind = tc::kStepHeadCol; cs.aux_ksteps = 0; cs.h_ksteps = kWidth / 16; cs.bias_off = 0; cs.post = 0;
-  S->pack.chunk0[n_hidden + 1] = chunk;
-  chunk += 2;
+  // the four head-weight chunks ((ddf,aux) hi, lo, colour hi, lo) follow the streamed chunks; the
+  // kernel copies them to shared memory once
+  S->pack.chunk0[n_hidden] = chunk;
+  S->pack.chunk0[n_hidden + 1] = chunk + 2;
   S->n_steps = si;
   S->chunks_per_tile = chunk;
   {
@@ -1137,11 +1149,7 @@ static int32_t tc_ensure(neddf_field* f) {
     // after the first colour layer's epilogue AUX is dead again: next tile's prologue goes there
     S->step[first_col].post = 2;
   }
-  if (const char* e = std::getenv("NEDDF_TC_CLUSTER")) {
-    int c = std::atoi(e);
-    if (c == 1 || c == 2 || c == 4) S->cluster = c;
-  }
-  if (cudaMalloc(&S->d_w, (size_t)chunk * tc::kStageBytes) != cudaSuccess ||
+  if (cudaMalloc(&S->d_w, (size_t)(chunk + 4) * tc::kChunkBytes) != cudaSuccess ||
       cudaMalloc(&S->d_bias, (size_t)n_hidden * kWidth * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess) {
     delete S;
@@ -1194,30 +1202,10 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
   P.timeline = S->timeline;
   P.timeline_cap = S->timeline_cap;
   int64_t n_tiles = (p.n + tc::kTileS - 1) / tc::kTileS;
-  int cluster = S->cluster;
-  int grid = (int)std::min<int64_t>((n_tiles + cluster - 1) / cluster * cluster, sm_count() / cluster * cluster);
-  if (n_tiles < 2 * cluster) {  // tiny launches: no point in pairing CTAs
-    cluster = 1;
-    grid = (int)std::min<int64_t>(n_tiles, sm_count());
-  }
-  P.cluster = cluster;
-  P.debug = 0;
-  if (const char* e = std::getenv("NEDDF_TC_DEBUG")) P.debug = std::atoi(e);
+  int grid = (int)std::min<int64_t>(n_tiles, sm_count());
   auto launch = [&](auto kern) -> int32_t {
     NEDDF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(tc::kThreads);
-    cfg.dynamicSmemBytes = tc::kSmemBytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    NEDDF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, P));
+    kern<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(P);
     NEDDF_LAUNCH_CHECK();
     return NEDDF_OK;
   };
