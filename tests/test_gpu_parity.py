@@ -279,3 +279,72 @@ def test_errors_are_loud():
             render.render_rays(c.t("uv").to(G.DEV), cam, uniforms=(torch.rand(3, 65), torch.rand(3, 129)))
     with pytest.raises(NotImplementedError):
         neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeRF"})
+
+
+def _bench_render(engine):
+    import bench
+    import neddf_b200
+    import tests.gpu_util as G
+    sd, p, fc = bench.seeded_state_dict()
+    render = neddf_b200.NeRFRender(network_config=bench.NET_CFG, **bench.RENDER_CFG)
+    render.load_state_dict(sd)
+    render.to(G.DEV)
+    render.set_iter(-1)
+    render.set_engine(engine)
+    R, T, calib = bench.synthetic_pose(0)
+    cam = neddf_b200.Camera.from_matrix(neddf_b200.PinholeCalib(calib), R, T).to(G.DEV)
+    cam.update_transform()
+    return render, cam
+
+
+def test_full_frame_properties():
+    """BASELINE.json full size (800x800, 64+128): size-independent properties of the render."""
+    import bench
+    render, cam = _bench_render("auto")
+    torch.manual_seed(0)
+    img = render.render_image(bench.W, bench.H, cam, ["color", "depth", "transmittance"], 1, 1024)
+    for k, c in (("color", 3), ("depth", 1), ("transmittance", 1)):
+        assert img[k].shape == (bench.H, bench.W, c)
+        assert bool(torch.isfinite(img[k]).all()), k
+    t = img["transmittance"]
+    assert float(t.min()) >= 0.0 and float(t.max()) <= 1.0 + 1e-3  # ReLU density: o in [0,1)
+    d = img["depth"]
+    assert float(d.min()) >= 2.0 - 1e-3 and float(d.max()) <= 6.1  # between near and max_dist
+
+
+def test_partition_of_unity_and_sorted_samples_at_full_chunk():
+    """sum(weights) + transmittance == 1 (up to the reference's +1e-7 per factor) on a 65,536-ray
+    chunk; fine distances sorted and inside [near, far + jitter]."""
+    import bench
+    G = _gpu()
+    render, cam = _bench_render("auto")
+    n = 65536
+    uv = orc.image_uv(bench.W, bench.H)[200 * bench.W:200 * bench.W + n].to(G.DEV)
+    torch.manual_seed(1)
+    with torch.no_grad():
+        out = render.render_rays(uv, cam)
+    s = out["weight"].sum(1) + out["transmittance"]
+    assert float((s - 1).abs().max()) < 2e-4
+    sc = out["weight_coarse"].sum(1) + out["transmittance_coarse"]
+    assert float((sc - 1).abs().max()) < 1e-4
+    assert bool((out["weight"] >= 0).all())
+
+
+def test_engines_agree_on_bench_workload():
+    """tcgen05 engine vs the fp32 FMA engine (device oracle) on 2,048 rays of the bench frame."""
+    import bench
+    G = _gpu()
+    r_tc, cam = _bench_render("tc")
+    r_32, _ = _bench_render("fp32")
+    n = 2048
+    uv = orc.image_uv(bench.W, bench.H)[400 * bench.W + 300:400 * bench.W + 300 + n].to(G.DEV)
+    g = torch.Generator().manual_seed(2)
+    u = (torch.rand(n, 65, generator=g).to(G.DEV), torch.rand(n, 129, generator=g).to(G.DEV))
+    with torch.no_grad():
+        a = r_tc.render_rays(uv, cam, uniforms=u)
+        b = r_32.render_rays(uv, cam, uniforms=u)
+        a2 = r_tc.render_rays(uv, cam, uniforms=u)
+    for k in ("color", "depth", "transmittance", "fields_penalty", "color_coarse", "weight_coarse"):
+        assert nerr(a[k].cpu().numpy(), b[k].cpu().numpy()) < PARITY_TOL, k
+    for k in a:
+        assert torch.equal(a[k], a2[k]), k  # deterministic / idempotent
