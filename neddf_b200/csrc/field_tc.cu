@@ -11,6 +11,10 @@
 // TF32's tensor rate.  fp16's range (65504) is checked in the epilogue; a tile that exceeds it sets
 // status bit 2 and the host raises (the fp32 engine covers such networks).
 //
+// Row order inside a 32-sample tile is type-major: row = 32*j + s (j = 0 value, 1..3 = d/dx,
+// d/dy, d/dz), so the value rows are the first 32 rows of every operand: when only images are
+// wanted (no fields_penalty) the colour trunk runs on N = 32 rows instead of 128.
+//
 // Orientation.  Every sample carries 4 rows (value + d/dx, d/dy, d/dz).  The MMAs are issued
 // "swapped": A = weights (M = 128 output channels, K-major), B = activations (N = 128 rows =
 // 32 samples x 4, MN-major), so the accumulator has one output channel per TMEM lane and the four
@@ -72,6 +76,7 @@ constexpr uint32_t kOffScratch = kOffHeadW + 4 * kChunkBytes;
 struct Scratch {
   float geo[kTileS][12];   // pos[3], dir[3], var[3], pad
   HeadOut head[kTileS];
+  float hgather[4][kTileS][4];  // head results per row type (lane quarter) and sample
   uint64_t a_full[kARing];   // loaders -> MMA: chunk written to tensor memory
   uint64_t a_empty[kARing];  // MMA -> loaders: chunk consumed
   uint64_t act_ready[2];  // epilogue group h -> MMA: accumulator h drained, H[k-half h] rewritten
@@ -103,6 +108,8 @@ struct TcParams {
   const unsigned char* w_tc;  // packed chunks, kStageBytes each, in consumption order
   const float* bias;          // [n_hidden][256] plain channel order
   int* status;
+  int head_da_step;     // index of the distance/aux heads step
+  int eval;             // 1 = images only: colour trunk on value rows (N = 32), no penalty / colour Jacobian
   long long* timeline;  // optional: CTA 0 writes 6 values per step (profiling aid)
   int timeline_cap;
 };
@@ -205,6 +212,7 @@ constexpr uint32_t kIdescHidden = make_idesc(128, kRows, 0, 1);      // A weight
 // B = [hi rows | lo rows]: the lo buffer starts exactly 16 row-groups after the hi buffer, so one
 // N = 256 MMA produces A_hi*B_hi (columns 0-127) and A_hi*B_lo (columns 128-255) together
 constexpr uint32_t kIdescHiddenWide = make_idesc(128, 2 * kRows, 0, 1);
+constexpr uint32_t kIdescHiddenValue = make_idesc(128, kTileS, 0, 1);  // value rows only (eval colour trunk)
 constexpr uint32_t kIdescHead = make_idesc(kRows, 16, 1, 0);     // A activations MN-major, B head weights K-major
 
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -298,6 +306,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
   uint32_t r[4];
   asm volatile(
@@ -361,15 +380,25 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
 }
 
-// write the 4 rows (value, Jx, Jy, Jz) of sample s, K index k into an operand buffer pair
+// write the rows (value, Jx, Jy, Jz) of sample s at K index k into an operand buffer pair;
+// type-major row order: row = 32*j + s.  rows = 4, or 1 when only the value row is consumed.
 __device__ __forceinline__ void store_sample(unsigned char* hi_buf, unsigned char* lo_buf, int KC, int s, int k,
-                                             float v0, float v1, float v2, float v3, float& bad) {
+                                             float v0, float v1, float v2, float v3, float& bad, int rows = 4) {
   uint32_t h0, l0, h1, l1;
   split2(v0, v1, h0, l0, bad);
   split2(v2, v3, h1, l1, bad);
-  uint32_t off = act_off(4 * s, k, KC);
-  *reinterpret_cast<uint2*>(hi_buf + off) = make_uint2(h0, h1);
-  *reinterpret_cast<uint2*>(lo_buf + off) = make_uint2(l0, l1);
+  const uint32_t off = act_off(s, k, KC);
+  const uint32_t tstride = (uint32_t)(4 * KC * 16);  // 32 rows = 4 row groups
+  *reinterpret_cast<uint16_t*>(hi_buf + off) = (uint16_t)(h0 & 0xffffu);
+  *reinterpret_cast<uint16_t*>(lo_buf + off) = (uint16_t)(l0 & 0xffffu);
+  if (rows > 1) {
+    *reinterpret_cast<uint16_t*>(hi_buf + off + tstride) = (uint16_t)(h0 >> 16);
+    *reinterpret_cast<uint16_t*>(lo_buf + off + tstride) = (uint16_t)(l0 >> 16);
+    *reinterpret_cast<uint16_t*>(hi_buf + off + 2 * tstride) = (uint16_t)(h1 & 0xffffu);
+    *reinterpret_cast<uint16_t*>(lo_buf + off + 2 * tstride) = (uint16_t)(l1 & 0xffffu);
+    *reinterpret_cast<uint16_t*>(hi_buf + off + 3 * tstride) = (uint16_t)(h1 >> 16);
+    *reinterpret_cast<uint16_t*>(lo_buf + off + 3 * tstride) = (uint16_t)(l1 >> 16);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,7 +441,7 @@ __device__ __forceinline__ void tile_geometry(const FieldParams& p, Scratch* sc,
 // (neddf.py:200-204) else plain (neddf.py:205-209).  `sub`/`nsub` split the 3*E entries.
 __device__ __forceinline__ void write_pos_embedding(const FieldParams& p, const Scratch* sc, unsigned char* aux_hi,
                                                     unsigned char* aux_lo, int s, int sub, int nsub, bool scaled,
-                                                    float& bad) {
+                                                    float& bad, int rows = 4) {
   const int half = 3 * p.embed_pos;
   for (int idx = sub; idx < half; idx += nsub) {
     int e = idx / 3, d = idx - 3 * e;
@@ -423,8 +452,8 @@ __device__ __forceinline__ void write_pos_embedding(const FieldParams& p, const 
     float vs[4] = {sc_ * q.s, 0.f, 0.f, 0.f}, vc[4] = {sc_ * q.c, 0.f, 0.f, 0.f};
     vs[1 + d] = js;
     vc[1 + d] = jc;
-    store_sample(aux_hi, aux_lo, kAuxK, s, idx, vs[0], vs[1], vs[2], vs[3], bad);
-    store_sample(aux_hi, aux_lo, kAuxK, s, half + idx, vc[0], vc[1], vc[2], vc[3], bad);
+    store_sample(aux_hi, aux_lo, kAuxK, s, idx, vs[0], vs[1], vs[2], vs[3], bad, rows);
+    store_sample(aux_hi, aux_lo, kAuxK, s, half + idx, vc[0], vc[1], vc[2], vc[3], bad, rows);
   }
 }
 
@@ -566,6 +595,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           const int nA = st.aux_ksteps, n1 = st.h_ksteps / 2, n0 = nA + st.h_ksteps - n1;
           const uint64_t dba_hi = make_desc(s_ahi, 128, kAuxK * 16), dba_lo = make_desc(s_alo, 128, kAuxK * 16);
           const uint64_t dbh_hi = make_desc(s_hhi, 128, kHK * 16), dbh_lo = make_desc(s_hlo, 128, kHK * 16);
+          // images only: the colour trunk (every hidden step after the distance heads) needs no
+          // Jacobian rows - the value rows are rows 0..31 of the same operands
+          const uint32_t idesc = (P.eval && si > P.head_da_step) ? kIdescHiddenValue : kIdescHidden;
           auto issue = [&](int half, int ks_begin, int ks_end) {
             const uint32_t d = tmem + half * kRows;
             for (int ks = ks_begin; ks < ks_end; ++ks) {
@@ -576,9 +608,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
               if (stamp) waited += clock64() - w0;
               tc_fence_after();
               const uint32_t a = tmem + kACol + stage * 16;
-              mma_f16_ts_elect(d, a, db_hi, kIdescHidden, ks > 0);
-              mma_f16_ts_elect(d, a + 8, db_hi, kIdescHidden, 1);
-              mma_f16_ts_elect(d, a, db_lo, kIdescHidden, 1);
+              mma_f16_ts_elect(d, a, db_hi, idesc, ks > 0);
+              mma_f16_ts_elect(d, a + 8, db_hi, idesc, 1);
+              mma_f16_ts_elect(d, a, db_lo, idesc, 1);
               mma_commit_elect(&sc->a_empty[stage]);
               if (++stage == kARing) {
                 stage = 0;
@@ -640,17 +672,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     // colour-trunk inputs E0 | D (| zero pad) into AUX (neddf.py:205-210, 243); 16 threads per sample
     auto colour_prep = [&]() {
       const int s = tid >> 4, sub = tid & 15;
-      write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 16, false, bad);
+      const int rows = P.eval ? 1 : 4;
+      write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 16, false, bad, rows);
       const int dhalf = 3 * p.embed_dir;
       for (int idx = sub; idx < dhalf; idx += 16) {
         int e = idx / 3, d = idx - 3 * e;
         float sn, cs;
         sincosf((float)(1u << e) * sc->geo[s][3 + d], &sn, &cs);
-        store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + idx, sn, 0.f, 0.f, 0.f, bad);
-        store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + dhalf + idx, cs, 0.f, 0.f, 0.f, bad);
+        store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + idx, sn, 0.f, 0.f, 0.f, bad, rows);
+        store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + dhalf + idx, cs, 0.f, 0.f, 0.f, bad, rows);
       }
       for (int k = p.n_e0 + p.n_d + 3 + sub; k < kAuxK; k += 16)
-        store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
+        store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad, rows);
     };
     if (my_tiles > 0) {
       prologue(blockIdx.x);
@@ -675,38 +708,50 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         if (st.kind == kStepHidden) {
           const float bias = __ldg(P.bias + st.bias_off + ch);
           const uint32_t tbase = tmem + lane_addr + half * kRows;
+          const bool value_only = P.eval && si > P.head_da_step;
 #pragma unroll 1
-          for (int cb = 4 * shalf; cb < 4 * shalf + 4; ++cb) {  // 16 columns = 4 samples per load
-            float v[16];
-            tmem_ld16(tbase + cb * 16, v);
+          for (int blk = 0; blk < 2; ++blk) {  // 8 samples = one 16-byte row group per row type
+            const int s0 = 16 * shalf + 8 * blk;
+            float x[8], d1[8];
+            tmem_ld8(tbase + s0, x);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {  // 2 samples = one 16-byte row group
-              float y0, d0, y1, d1;
-              tc_hidden_act<ACT>(v[8 * q + 0] + bias, y0, d0);
-              tc_hidden_act<ACT>(v[8 * q + 4] + bias, y1, d1);
-              uint32_t h[4], l[4];
-              split2(y0, d0 * v[8 * q + 1], h[0], l[0], bad);
-              split2(d0 * v[8 * q + 2], d0 * v[8 * q + 3], h[1], l[1], bad);
-              split2(y1, d1 * v[8 * q + 5], h[2], l[2], bad);
-              split2(d1 * v[8 * q + 6], d1 * v[8 * q + 7], h[3], l[3], bad);
-              const uint32_t off = (uint32_t)((2 * cb + q) * (kHK * 16) + ch * 16);
-              *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            for (int i = 0; i < 8; ++i) tc_hidden_act<ACT>(x[i] + bias, x[i], d1[i]);
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split2(x[2 * i], x[2 * i + 1], h[i], l[i], bad);
+            uint32_t off = (uint32_t)((s0 >> 3) * (kHK * 16) + ch * 16);
+            *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            if (!value_only) {
+#pragma unroll
+              for (int j = 1; j < 4; ++j) {  // Jacobian rows: G = f'(x) J (tanh_exp.py:47-48)
+                float g[8];
+                tmem_ld8(tbase + 32 * j + s0, g);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2(d1[2 * i] * g[2 * i], d1[2 * i + 1] * g[2 * i + 1], h[i], l[i], bad);
+                off += 4 * (kHK * 16);
+                *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+              }
             }
           }
         } else if (st.kind == kStepHeadDA) {
           if (warp < 4) {
-            // one row per lane: columns 0,1 = ddf_out, aux_out of that row (neddf.py:220-230)
+            // lane quarter j = row type j, lane = sample: columns 0,1 = ddf_out, aux_out of that row
+            // (neddf.py:220-230); the four types of a sample meet through shared memory
             float v[4];
             tmem_ld4(tmem + lane_addr + kHeadCol, v);
-            float ddf[4], aux[4];
+            sc->hgather[quarter][lane][0] = v[0];
+            sc->hgather[quarter][lane][1] = v[1];
+            asm volatile("bar.sync 4, 128;" ::: "memory");
+            if (warp == 0) {
+              const int s = lane;
+              float ddf[4], aux[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              ddf[j] = __shfl_down_sync(0xffffffffu, v[0], j);
-              aux[j] = __shfl_down_sync(0xffffffffu, v[1], j);
-            }
-            if ((lane & 3) == 0) {
-              const int s = 8 * quarter + (lane >> 2);
+              for (int j = 0; j < 4; ++j) {
+                ddf[j] = sc->hgather[j][s][0];
+                aux[j] = sc->hgather[j][s][1];
+              }
               ddf[0] += __ldg(p.b_head + 0);
               aux[0] += __ldg(p.b_head + 1);
               HeadOut h;
@@ -714,7 +759,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
               sc->head[s] = h;
               const int kn = p.n_e0 + p.n_d;  // normal: detached, zero Jacobian (neddf.py:243-253)
 #pragma unroll
-              for (int i = 0; i < 3; ++i) store_sample(aux_hi, aux_lo, kAuxK, s, kn + i, h.normal[i], 0.f, 0.f, 0.f, bad);
+              for (int i = 0; i < 3; ++i)
+                store_sample(aux_hi, aux_lo, kAuxK, s, kn + i, h.normal[i], 0.f, 0.f, 0.f, bad, P.eval ? 1 : 4);
             }
           }
           if (st.post == 1) colour_prep();  // only when no earlier MMA phase could hide it
@@ -723,21 +769,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           if (warp < 4) {
             float v[4];
             tmem_ld4(tmem + lane_addr + kHeadCol, v);
-            float cv[4][3];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) cv[j][c] = __shfl_down_sync(0xffffffffu, v[c], j);
-            const int s = 8 * quarter + (lane >> 2);
+            sc->hgather[quarter][lane][0] = v[0];
+            sc->hgather[quarter][lane][1] = v[1];
+            sc->hgather[quarter][lane][2] = v[2];
+            asm volatile("bar.sync 4, 128;" ::: "memory");
+            const int s = lane;
             const int64_t n = n0 + s;
-            if ((lane & 3) == 0 && n < p.n) {
+            if (warp == 0 && n < p.n) {
               const HeadOut& h = sc->head[s];
               float col[3], colJ[3][3];
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                col[c] = cv[0][c] + __ldg(p.b_head + 2 + c);
+                col[c] = sc->hgather[0][s][c] + __ldg(p.b_head + 2 + c);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) colJ[i][c] = cv[1 + i][c];
+                for (int i = 0; i < 3; ++i) colJ[i][c] = sc->hgather[1 + i][s][c];
               }
               if (p.distance) p.distance[n] = h.distance;
               if (p.density) p.density[n] = h.density;
@@ -747,6 +792,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                 p.color[3 * n + 1] = col[1];
                 p.color[3 * n + 2] = col[2];
               }
+              // (in images-only mode the colour Jacobian rows are not computed and no penalty is asked)
               if (p.penalty) p.penalty[n] = field_penalty(h, col, colJ, p.distance_range_max, p.penalty_weight);
             }
           }
@@ -840,6 +886,7 @@ struct TcStorage {
   TcPackArgs pack;
   long long* timeline = nullptr;
   int timeline_cap = 0;
+  int head_da_step = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1144,6 +1191,7 @@ static int32_t tc_ensure(neddf_field* f) {
       if (head_da < 0 && S->step[i].kind == tc::kStepHidden && S->step[i].aux_ksteps > 0) last_aux = i;
       if (head_da >= 0 && first_col < 0 && S->step[i].kind == tc::kStepHidden) first_col = i;
     }
+    S->head_da_step = head_da;
     if (last_aux + 1 < head_da) S->step[last_aux].post = 1;
     else S->step[head_da].post = 1;
     // after the first colour layer's epilogue AUX is dead again: next tile's prologue goes there
@@ -1188,7 +1236,6 @@ int32_t tc_pack_weights(neddf_field* f, const float* const* d_w, const float* co
 }
 
 int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStream_t s) {
-  (void)flags;
   tc::TcStorage* S = static_cast<tc::TcStorage*>(f->tc);
   if (!S) return fail(NEDDF_E_INVALID, "tensor-core engine: weights were never packed");
   tc::TcParams P;
@@ -1199,6 +1246,8 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
   P.w_tc = S->d_w;
   P.bias = S->d_bias;
   P.status = S->d_status;
+  P.eval = (flags == NEDDF_OUT_EVAL && p.penalty == nullptr) ? 1 : 0;
+  P.head_da_step = S->head_da_step;
   P.timeline = S->timeline;
   P.timeline_cap = S->timeline_cap;
   int64_t n_tiles = (p.n + tc::kTileS - 1) / tc::kTileS;
