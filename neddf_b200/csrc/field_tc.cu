@@ -16,26 +16,33 @@
 // wanted (no fields_penalty) the colour trunk runs on N = 32 rows instead of 128.
 //
 // Orientation.  Every sample carries 4 rows (value + d/dx, d/dy, d/dz).  The MMAs are issued
-// "swapped": A = weights (M = 128 output channels, K-major), B = activations (N = 128 rows =
-// 32 samples x 4, MN-major), so the accumulator has one output channel per TMEM lane and the four
-// rows of a sample in four adjacent columns.  The epilogue thread that owns a channel therefore
-// holds x and its three Jacobian entries in registers: y = f(x), G = f'(x) J need no cross-thread
-// traffic, and it writes 8 consecutive rows (16 bytes) of the next layer's B operand per store.
-// The narrow heads (256->1,1,3) run in the standard orientation (A = activations, N = 16) so that
-// their result has one sample row per lane.
+// "swapped": A = weights (M = 128 output channels), B = activations (N = 128 rows = 32 samples x 4,
+// MN-major in shared memory), so the accumulator has one output channel per TMEM lane and the rows
+// of a sample in columns.  The epilogue thread that owns a channel therefore holds x and its three
+// Jacobian entries in registers: y = f(x), G = f'(x) J need no cross-thread traffic, and it writes
+// 8 consecutive rows (16 bytes) of the next layer's B operand per store.  The narrow heads
+// (256->1,1,3) run in the standard orientation (A = activations, N = 16) so that their result has
+// one sample row per lane.
 //
-// Per SM: one CTA of 18 warps, persistent over 32-sample tiles.
-//   warps 0-15 epilogue: TMEM -> registers (tcgen05.ld), bias + activation + Jacobian, fp16
-//              hi/lo split, st.shared into the next B operand; also prologue (geometry, PE).
-//              warp w: TMEM lane quarter w%4, channel half (w/4)%2, sample half w/8
-//   warp  16   TMA producer: cp.async.bulk of 8 KB weight chunks through a 5-stage ring
-//   warp  17   MMA issuer: one thread, tcgen05.mma + tcgen05.commit onto mbarriers
+// A operand in tensor memory.  With A in shared memory a 128xNx16 tcgen05.mma costs ~133 cycles for
+// any N <= 256 (the A fetch sets the rate, tools/mma_bench.py); with A in tensor memory it costs
+// the 64-cycle floor (tools/ts_test.py).  The weights therefore never enter shared memory: loader
+// warps read each 8 KB chunk from L2 (LDG.128, prefetched in registers) and write it into a
+// 16-stage ring of TMEM columns with tcgen05.st.
+//
+// Per SM: one CTA of 25 warps, persistent over 32-sample tiles.
+//   warps 0-15  epilogue: TMEM -> registers (tcgen05.ld), bias + activation + Jacobian, fp16
+//               hi/lo split, st.shared into the next B operand; also prologue (geometry, PE).
+//               warp w: TMEM lane quarter w%4, channel half (w/4)%2 (= epilogue group), sample
+//               half w/8
+//   warp  16    MMA issuer: convergent warp, one elected lane issues tcgen05.mma / tcgen05.commit
+//   warps 17-24 weight loaders: L2 -> registers -> tensor memory, two warps per lane quarter
 // Shared memory (B operands, canonical no-swizzle MN-major: [row/8][k][row%8] fp16):
 //   H   hi/lo  128 rows x 256 k   2 x 64 KB   hidden activations, rewritten layer after layer
 //   AUX hi/lo  128 rows x  96 k   2 x 24 KB   E_s (trunk input + skip) then [E0|D|n] (colour input)
-//   W ring     5 x 8 KB                      weight chunks [hi 4 KB | lo 4 KB], K-major
-// TMEM: channel half h at columns [256h, 256h+256): [0,128) = A_hi*B_hi + A_lo*B_hi, [128,256) =
-// A_hi*B_lo (summed in the epilogue); head results alias columns [0,16).
+//   head weights 4 x 8 KB (resident)
+// TMEM (512 columns): accumulator of channel half h at [128h, 128h+128); head results alias
+// columns [0,16); weight ring at [256, 512), 16 columns (8 hi + 8 lo) per chunk.
 #include "field_math.cuh"
 
 #include <cuda_fp16.h>
@@ -86,8 +93,6 @@ struct Scratch {
 };
 constexpr uint32_t kSmemBytes = kOffScratch + sizeof(Scratch);
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-static_assert(kOffHLo == kOffHHi + 16 * (kHK * 16) && kOffAuxLo == kOffAuxHi + 16 * (kAuxK * 16),
-              "lo buffers must follow the hi buffers at exactly 16 row-groups (wide-N MMA)");
 
 enum StepKind { kStepHidden = 0, kStepHeadDA = 1, kStepHeadCol = 2 };
 
@@ -141,9 +146,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -156,30 +158,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// multicast variant: the chunk lands at the same offset in every CTA of `mask`, and each of
-// those CTAs' own barrier (same offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -209,9 +187,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(M >> 4) << 24);
 }
 constexpr uint32_t kIdescHidden = make_idesc(128, kRows, 0, 1);      // A weights K-major, B activations MN-major
-// B = [hi rows | lo rows]: the lo buffer starts exactly 16 row-groups after the hi buffer, so one
-// N = 256 MMA produces A_hi*B_hi (columns 0-127) and A_hi*B_lo (columns 128-255) together
-constexpr uint32_t kIdescHiddenWide = make_idesc(128, 2 * kRows, 0, 1);
 constexpr uint32_t kIdescHiddenValue = make_idesc(128, kTileS, 0, 1);  // value rows only (eval colour trunk)
 constexpr uint32_t kIdescHead = make_idesc(kRows, 16, 1, 0);     // A activations MN-major, B head weights K-major
 
@@ -269,24 +244,6 @@ __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
       "elect.sync _|q, 0xffffffff;\n"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
       "}\n" ::"r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_mc_elect(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "h"(mask)
-      : "memory");
-}
-// arrive on the barrier at the same offset in every CTA of `mask`
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
