@@ -179,6 +179,17 @@ int32_t neddf_composite(const float* d_dists, const float* d_density, const floa
                         float* d_transmittance, float* d_penalty_out, int32_t* d_status,
                         void* stream);
 
+/* Backward of neddf_composite (what autograd derives through base_neural_render.py:148-172 and
+ * nerf_render.py:153-159 in the reference).  Upstream gradients g_* of weight[n_rays,n_edges-1],
+ * depth[n_rays], color_out[n_rays,3], transmittance[n_rays], penalty_out[n_rays] (any may be NULL =
+ * zero) -> gradients of density[n_rays,n_edges], color[n_rays,n_edges,3], penalty[n_rays,n_edges]
+ * (any may be NULL).  Edge distances carry no gradient (the reference samples them under no_grad). */
+int32_t neddf_composite_backward(const float* d_dists, const float* d_density, const float* d_color,
+                                 int64_t n_rays, int32_t n_edges, float max_dist, const float* g_weight,
+                                 const float* g_depth, const float* g_color, const float* g_transmittance,
+                                 const float* g_penalty, float* d_grad_density, float* d_grad_color,
+                                 float* d_grad_penalty, void* stream);
+
 /* BaseNeuralRender.sample_pdf with cat_coarse=True (base_neural_render.py:27-115).
  * in : dists[n_rays,n_edges], weights[n_rays,n_edges-1] (IN/OUT: negative and NaN entries are
  *      zeroed in place exactly as the reference does to its argument, :52-55), u[n_rays,n_new]

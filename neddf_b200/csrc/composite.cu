@@ -95,9 +95,146 @@ composite_kernel(const float* __restrict__ dists, const float* __restrict__ dens
   if (status && __any_sync(0xffffffffu, saw_nan) && lane == 0) atomicOr(status, 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward of the compositing integral (training path; the reference gets it from autograd through
+// base_neural_render.py:148-172).  With o_j = 1 - exp(-sigma_j delta_j), f_j = 1 - o_j + 1e-7,
+// T_j = prod_{i<j} f_i, w_j = o_j T_j and upstream gradients g_w, g_depth, g_color, g_T, g_pen:
+//   G_j      = g_w[j] + g_depth d_j + g_color . c_j                (dL/dw_j)
+//   dL/do_i  = G_i T_i - (sum_{j>i} G_j w_j + g_Tlast T_last) / f_i,  g_Tlast = g_depth max_dist + g_T
+//   dL/dsigma_i = dL/do_i * delta_i * (1 - o_i),  dL/dc_i = w_i g_color,  dL/dp_i = delta_i g_pen
+// The last edge only closes the last interval and receives zero gradient.  One warp per ray: a
+// forward product scan (kept in shared memory) followed by a reverse sum scan.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_backward_kernel(const float* __restrict__ dists, const float* __restrict__ density,
+                          const float* __restrict__ color, int64_t n_rays, int n_edges, float max_dist,
+                          const float* __restrict__ g_weight, const float* __restrict__ g_depth,
+                          const float* __restrict__ g_color, const float* __restrict__ g_trans,
+                          const float* __restrict__ g_pen, float* __restrict__ d_density,
+                          float* __restrict__ d_color, float* __restrict__ d_penalty) {
+  extern __shared__ float smem_c[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int n_int = n_edges - 1;
+  float* s_T = smem_c + (size_t)wib * 2 * n_int;  // T_j
+  float* s_o = s_T + n_int;                       // o_j
+  const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + wib; ray < n_rays; ray += n_warps) {
+    const float* drow = dists + ray * n_edges;
+    const float* srow = density + ray * n_edges;
+    const float* crow = color + ray * n_edges * 3;
+    // forward scan (same arithmetic as composite_kernel)
+    double carry = 1.0;
+    for (int base = 0; base < n_int; base += 32) {
+      const int j = base + lane;
+      const bool live = j < n_int;
+      float o = 0.f;
+      if (live) {
+        float delta = drow[j + 1] - drow[j];
+        o = 1.0f - (float)exp((double)(-srow[j] * delta));
+      }
+      double incl = live ? (double)(1.0f - o + 1e-7f) : 1.0;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        double up = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= s) incl *= up;
+      }
+      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0;
+      if (live) {
+        s_T[j] = (float)(carry * excl);
+        s_o[j] = o;
+      }
+      carry = carry * __shfl_sync(0xffffffffu, incl, 31);
+    }
+    const float t_last = (float)carry;
+    __syncwarp();
+    const float gd = g_depth ? g_depth[ray] : 0.f;
+    const float gt = g_trans ? g_trans[ray] : 0.f;
+    const float gp = g_pen ? g_pen[ray] : 0.f;
+    float gc[3] = {0.f, 0.f, 0.f};
+    if (g_color) {
+      gc[0] = g_color[3 * ray + 0];
+      gc[1] = g_color[3 * ray + 1];
+      gc[2] = g_color[3 * ray + 2];
+    }
+    // reverse pass: suffix sums of G_j w_j, blocks of 32 from the far end
+    float suffix = (gd * max_dist + gt) * t_last;  // sum_{j>i} G_j w_j + g_Tlast T_last, running
+    const int n_blocks = (n_int + 31) / 32;
+    for (int blk = n_blocks - 1; blk >= 0; --blk) {
+      const int j = blk * 32 + lane;
+      const bool live = j < n_int;
+      float Gw = 0.f, G = 0.f, T = 0.f, o = 0.f, delta = 0.f, w = 0.f;
+      if (live) {
+        T = s_T[j];
+        o = s_o[j];
+        w = o * T;
+        const float dj = drow[j];
+        delta = drow[j + 1] - dj;
+        G = (g_weight ? g_weight[ray * n_int + j] : 0.f) + gd * dj + gc[0] * crow[3 * j] + gc[1] * crow[3 * j + 1] +
+            gc[2] * crow[3 * j + 2];
+        Gw = G * w;
+      }
+      // inclusive suffix scan within the block (towards higher lanes)
+      float incl = Gw;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        float dn = __shfl_down_sync(0xffffffffu, incl, s);
+        if (lane + s < 32) incl += dn;
+      }
+      const float after = incl - Gw + suffix;  // sum over j' > j (this block and later) + tail term
+      if (live) {
+        const float f = 1.0f - o + 1e-7f;
+        const float dldo = G * T - after / f;
+        if (d_density) d_density[ray * n_edges + j] = dldo * delta * (1.0f - o);
+        if (d_color) {
+          d_color[(ray * n_edges + j) * 3 + 0] = w * gc[0];
+          d_color[(ray * n_edges + j) * 3 + 1] = w * gc[1];
+          d_color[(ray * n_edges + j) * 3 + 2] = w * gc[2];
+        }
+        if (d_penalty) d_penalty[ray * n_edges + j] = delta * gp;
+      }
+      suffix += __shfl_sync(0xffffffffu, incl, 0);
+    }
+    if (lane == 0) {  // the closing edge
+      const int j = n_int;
+      if (d_density) d_density[ray * n_edges + j] = 0.f;
+      if (d_color) {
+        d_color[(ray * n_edges + j) * 3 + 0] = 0.f;
+        d_color[(ray * n_edges + j) * 3 + 1] = 0.f;
+        d_color[(ray * n_edges + j) * 3 + 2] = 0.f;
+      }
+      if (d_penalty) d_penalty[ray * n_edges + j] = 0.f;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace neddf
 
 using namespace neddf;
+
+extern "C" int32_t neddf_composite_backward(const float* d_dists, const float* d_density, const float* d_color,
+                                            int64_t n_rays, int32_t n_edges, float max_dist, const float* g_weight,
+                                            const float* g_depth, const float* g_color, const float* g_transmittance,
+                                            const float* g_penalty, float* d_grad_density, float* d_grad_color,
+                                            float* d_grad_penalty, void* stream) {
+  if (n_rays < 0 || n_edges < 2) return fail(NEDDF_E_INVALID, "neddf_composite_backward: bad sizes");
+  if (n_rays == 0) return NEDDF_OK;
+  if (!d_dists || !d_density || !d_color) return fail(NEDDF_E_INVALID, "neddf_composite_backward: null input pointer");
+  size_t smem = (size_t)kWarpsPerBlock * 2 * (n_edges - 1) * sizeof(float);
+  if (smem > 200 * 1024) return fail(NEDDF_E_UNSUPPORTED, "neddf_composite_backward: too many samples per ray");
+  if (smem > 48 * 1024)
+    NEDDF_CUDA_CHECK(cudaFuncSetAttribute(composite_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  composite_backward_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      d_dists, d_density, d_color, n_rays, n_edges, max_dist, g_weight, g_depth, g_color, g_transmittance, g_penalty,
+      d_grad_density, d_grad_color, d_grad_penalty);
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}
 
 extern "C" int32_t neddf_composite(const float* d_dists, const float* d_density, const float* d_color,
                                    const float* d_penalty, int64_t n_rays, int32_t n_edges, float max_dist,

@@ -59,6 +59,53 @@ def _camera_host(camera) -> Tuple[Any, Any, Any]:
     return L.fbuf(R), L.fbuf(T), L.fbuf(calib[:4])
 
 
+class _CompositeFn(torch.autograd.Function):
+    """Differentiable compositing: forward neddf_composite, backward neddf_composite_backward
+    (gradients w.r.t. densities, colours and penalties; edge distances carry none, like the
+    reference where they come from torch.rand / a no_grad resampling)."""
+
+    @staticmethod
+    def forward(ctx, dists, densities, colors, penalties, max_dist, status):
+        B, E = dists.shape
+        device = dists.device
+        weight = torch.empty(B, E - 1, device=device, dtype=torch.float32)
+        depth = torch.empty(B, device=device, dtype=torch.float32)
+        color = torch.empty(B, 3, device=device, dtype=torch.float32)
+        trans = torch.empty(B, device=device, dtype=torch.float32)
+        pen = torch.empty(B, device=device, dtype=torch.float32) if penalties is not None else None
+        with torch.cuda.device(device):
+            L.check(L.lib().neddf_composite(L.ptr(dists), L.ptr(densities), L.ptr(colors), L.ptr(penalties), B, E,
+                                            float(max_dist), L.ptr(weight), L.ptr(depth), L.ptr(color), L.ptr(trans),
+                                            L.ptr(pen), L.ptr(status), L.stream_ptr(device)), "composite")
+        ctx.save_for_backward(dists, densities, colors)
+        ctx.max_dist = float(max_dist)
+        ctx.has_pen = penalties is not None
+        if pen is None:
+            pen = torch.zeros(0, device=device)
+        return weight, depth, color, trans, pen
+
+    @staticmethod
+    def backward(ctx, g_w, g_d, g_c, g_t, g_p):
+        dists, densities, colors = ctx.saved_tensors
+        B, E = dists.shape
+        device = dists.device
+
+        def prep(g):
+            return None if g is None else g.contiguous().to(torch.float32)
+
+        g_w, g_d, g_c, g_t = prep(g_w), prep(g_d), prep(g_c), prep(g_t)
+        g_p = prep(g_p) if ctx.has_pen else None
+        d_dens = torch.empty_like(densities)
+        d_col = torch.empty_like(colors)
+        d_pen = torch.empty_like(densities) if ctx.has_pen else None
+        with torch.cuda.device(device):
+            L.check(L.lib().neddf_composite_backward(L.ptr(dists), L.ptr(densities), L.ptr(colors), B, E, ctx.max_dist,
+                                                     L.ptr(g_w), L.ptr(g_d), L.ptr(g_c), L.ptr(g_t), L.ptr(g_p),
+                                                     L.ptr(d_dens), L.ptr(d_col), L.ptr(d_pen), L.stream_ptr(device)),
+                    "composite_backward")
+        return None, d_dens, d_col, d_pen, None, None
+
+
 class BaseNeuralRender(nn.Module):
     """neddf/render/base_neural_render.py:11-194 (CUDA-backed sample_pdf / integrate_volume_render)."""
 
@@ -105,13 +152,21 @@ class BaseNeuralRender(nn.Module):
                                 penalties: Optional[Tensor] = None) -> Dict[str, Tensor]:
         """Alpha compositing (base_neural_render.py:117-172); with ``penalties`` also the
         per-ray penalty integral of render_rays (nerf_render.py:153-159)."""
-        if torch.is_grad_enabled() and (densities.requires_grad or colors.requires_grad):
-            raise NotImplementedError("neddf_b200: differentiable compositing is not built yet")
         dists = L.require_cuda_f32(dists, "dists")
         densities = L.require_cuda_f32(densities, "densities")
         colors = L.require_cuda_f32(colors, "colors")
         B, E = dists.shape
         device = dists.device
+        if torch.is_grad_enabled() and (densities.requires_grad or colors.requires_grad or
+                                        (penalties is not None and penalties.requires_grad)):
+            if penalties is not None:
+                penalties = L.require_cuda_f32(penalties, "penalties")
+            w, d, c, t, p_ = _CompositeFn.apply(dists.detach(), densities, colors, penalties, self.max_dist,
+                                                self._status(device))
+            res = {"weight": w, "depth": d, "color": c, "transmittance": t}
+            if penalties is not None:
+                res["fields_penalty"] = p_
+            return res
         res = {
             "weight": torch.empty(B, E - 1, device=device, dtype=torch.float32),
             "depth": torch.empty(B, device=device, dtype=torch.float32),

@@ -447,3 +447,38 @@ def test_weights_repacked_after_in_place_update():
     ref = orc.render_rays(p2, p2, c.fc, c.st, c.rc, c.t("uv"), c.cam, c.t("u_coarse"), c.t("u_fine"))
     for k in ("color", "depth", "transmittance"):
         assert nerr(b[k].cpu().numpy(), ref[k].numpy()) < PARITY_TOL, k
+
+
+@pytest.mark.parametrize("name", ["bunny", "default"])
+def test_composite_backward_matches_autograd(name):
+    """neddf_composite_backward against autograd through the oracle's restatement of
+    integrate_volume_render + penalty integration (what the reference's training step
+    differentiates, base_neural_render.py:148-172, nerf_render.py:153-159)."""
+    G = _gpu()
+    c = Case(name)
+    render = G.build_render(c)
+    dists = c.t("dists_fine")
+    dens = c.t("field_fine_density").clone().requires_grad_(True)
+    col = c.t("field_fine_color").clone().requires_grad_(True)
+    pen = c.t("field_fine_fields_penalty").clone().requires_grad_(True)
+    g = torch.Generator().manual_seed(9)
+    B, E = dists.shape
+    gw, gd, gc = torch.randn(B, E - 1, generator=g), torch.randn(B, generator=g), torch.randn(B, 3, generator=g)
+    gt, gp = torch.randn(B, generator=g), torch.randn(B, generator=g)
+    ref = orc.composite(dists, dens, col, c.rc.max_dist)
+    ref_pen = orc.integrate_penalty(dists, pen)
+    loss = (ref["weight"] * gw).sum() + (ref["depth"] * gd).sum() + (ref["color"] * gc).sum() + \
+        (ref["transmittance"] * gt).sum() + (ref_pen * gp).sum()
+    loss.backward()
+    dd = dens.detach().to(G.DEV).requires_grad_(True)
+    cd = col.detach().to(G.DEV).requires_grad_(True)
+    pd = pen.detach().to(G.DEV).requires_grad_(True)
+    out = render.integrate_volume_render(dists.to(G.DEV), dd, cd, pd)
+    l2 = (out["weight"] * gw.to(G.DEV)).sum() + (out["depth"] * gd.to(G.DEV)).sum() + (out["color"] * gc.to(G.DEV)).sum() + \
+        (out["transmittance"] * gt.to(G.DEV)).sum() + (out["fields_penalty"] * gp.to(G.DEV)).sum()
+    l2.backward()
+    assert abs(float(l2) - float(loss)) < 1e-4 * abs(float(loss)) + 1e-5
+    assert nerr(dd.grad.cpu().numpy(), dens.grad.numpy()) < 2e-5
+    assert nerr(cd.grad.cpu().numpy(), col.grad.numpy()) < 2e-5
+    assert nerr(pd.grad.cpu().numpy(), pen.grad.numpy()) < 2e-5
+    assert float(dd.grad[:, -1].abs().max()) == 0.0  # the closing edge receives no gradient
