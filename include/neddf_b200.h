@@ -166,6 +166,33 @@ int32_t neddf_field_forward_rays(const neddf_field_t* f, const neddf_field_state
                                  float* d_density, float* d_color, float* d_penalty,
                                  float* d_aux_grad, int32_t flags, int32_t engine, void* stream);
 
+/* Training forward (fp32 engine) of NeDDF.forward on rays + edge distances: like
+ * neddf_field_forward_rays with NEDDF_OUT_FULL, and additionally keeps the pre-activations of every
+ * hidden layer in d_save_pre [n_hidden][n][4][256] (n = n_rays*n_edges; value row incl. bias, then the
+ * three Jacobian rows) for neddf_field_backward. */
+int32_t neddf_field_forward_train(const neddf_field_t* f, const neddf_field_state_t* st,
+                                  const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
+                                  int64_t n_rays, int32_t n_edges, int32_t sampling_type, float ray_radius,
+                                  float* d_density, float* d_color, float* d_penalty, float* d_save_pre,
+                                  void* stream);
+
+/* Backward of NeDDF.forward (the reference's hand-written backward passes, nn_module/with_grad
+ * linear.py:49-84, tanh_exp.py:57-88, softplus.py:55-89, sigmoid.py:49-83, and autograd through
+ * neddf.py:220-300).  Inputs: the forward's geometry, d_save_pre, and the upstream gradients of
+ * density[n], color[n,3], fields_penalty[n] (g_penalty may be NULL).  The kernel does all sample-local
+ * work and the data-gradient GEMMs; it writes what the weight-gradient GEMMs  gW_l = X_l^T G_l  need:
+ *   d_post [n_hidden][n][4][256]  post-activations (h part of the next layer's / the heads' input)
+ *   d_gpre [n_hidden][n][4][256]  gradient w.r.t. each layer's pre-activations (bias grad = sum of row 0)
+ *   d_ghead_da [n][4][2], d_ghead_col [n][4][4]  gradients w.r.t. the head outputs (value + Jacobian rows)
+ *   d_xes [n][4][6*embed_pos]     scaled position embedding (input of layer 0 and of skip layers)
+ *   d_xcol [n][4][6*(embed_pos+embed_dir)+3]   [E0 | D | normal] (input part of the first colour layer) */
+int32_t neddf_field_backward(const neddf_field_t* f, const neddf_field_state_t* st, const float* d_ray_dir,
+                             const float* d_ray_orig, const float* d_dists, int64_t n_rays, int32_t n_edges,
+                             int32_t sampling_type, float ray_radius, const float* d_save_pre,
+                             const float* g_density, const float* g_color, const float* g_penalty, float* d_post,
+                             float* d_gpre, float* d_ghead_da, float* d_ghead_col, float* d_xes, float* d_xcol,
+                             void* stream);
+
 /* BaseNeuralRender.integrate_volume_render (neddf/render/base_neural_render.py:117-172) plus
  * the penalty integration of render_rays (nerf_render.py:153-159).
  * in : dists[n_rays,n_edges], density[n_rays,n_edges], color[n_rays,n_edges,3],

@@ -244,6 +244,7 @@ extern "C" int32_t neddf_field_destroy(neddf_field_t* f) {
   cudaFree(f->d_w_head_da);
   cudaFree(f->d_w_head_col);
   cudaFree(f->d_b_head);
+  cudaFree(f->d_wt_hidden);
   delete f;
   return NEDDF_OK;
 }
@@ -278,6 +279,10 @@ extern "C" int32_t neddf_field_set_weights(neddf_field_t* f, const float* const*
   NEDDF_LAUNCH_CHECK();
   if (tc_supported(f)) {
     int32_t rc = tc_pack_weights(f, d_weights, d_biases, s);
+    if (rc != NEDDF_OK) return rc;
+  }
+  {
+    int32_t rc = pack_backward_weights(f, d_weights, s);
     if (rc != NEDDF_OK) return rc;
   }
   f->weights_set = true;
@@ -352,4 +357,61 @@ extern "C" int32_t neddf_field_forward_rays(const neddf_field_t* f, const neddf_
   p.n = n_rays * (int64_t)n_edges;
   p.distance = d_distance; p.density = d_density; p.color = d_color; p.penalty = d_penalty; p.aux_grad = d_aux_grad;
   return dispatch(f, p, flags, engine, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// training path (fp32 engine)
+// ---------------------------------------------------------------------------------------------
+static int32_t fill_rays(const neddf_field* f, const neddf_field_state_t* st, FieldParams& p, const float* d_ray_dir,
+                         const float* d_ray_orig, const float* d_dists, int64_t n_rays, int32_t n_edges,
+                         int32_t sampling_type, float ray_radius, const char* who) {
+  if (!f) return fail(NEDDF_E_INVALID, std::string(who) + ": field is NULL");
+  if (!f->weights_set) return fail(NEDDF_E_INVALID, std::string(who) + ": weights were never set");
+  if (n_rays <= 0 || n_edges < 1) return fail(NEDDF_E_INVALID, std::string(who) + ": bad sizes");
+  if (sampling_type != NEDDF_SAMPLING_POINT && sampling_type != NEDDF_SAMPLING_CONE)
+    return fail(NEDDF_E_INVALID, std::string(who) + ": unknown sampling type");
+  if (sampling_type == NEDDF_SAMPLING_CONE && n_edges < 2) return fail(NEDDF_E_INVALID, std::string(who) + ": cone sampling needs >= 2 edges");
+  if (!d_ray_dir || !d_ray_orig || !d_dists) return fail(NEDDF_E_INVALID, std::string(who) + ": NULL input pointer");
+  p = f->proto;
+  int32_t rc = fill_state(f, st, p);
+  if (rc != NEDDF_OK) return rc;
+  p.ray_dir = d_ray_dir; p.ray_orig = d_ray_orig; p.dists = d_dists;
+  p.n_edges = n_edges; p.sampling_type = sampling_type; p.ray_radius = ray_radius;
+  p.n = n_rays * (int64_t)n_edges;
+  return NEDDF_OK;
+}
+
+extern "C" int32_t neddf_field_forward_train(const neddf_field_t* f, const neddf_field_state_t* st,
+                                             const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
+                                             int64_t n_rays, int32_t n_edges, int32_t sampling_type, float ray_radius,
+                                             float* d_density, float* d_color, float* d_penalty, float* d_save_pre,
+                                             void* stream) {
+  FieldParams p;
+  int32_t rc = fill_rays(f, st, p, d_ray_dir, d_ray_orig, d_dists, n_rays, n_edges, sampling_type, ray_radius,
+                         "neddf_field_forward_train");
+  if (rc != NEDDF_OK) return rc;
+  if (!d_save_pre) return fail(NEDDF_E_INVALID, "neddf_field_forward_train: d_save_pre is NULL");
+  p.density = d_density; p.color = d_color; p.penalty = d_penalty;
+  p.save_pre = d_save_pre;
+  return launch_field_fp32(f, p, (cudaStream_t)stream);
+}
+
+extern "C" int32_t neddf_field_backward(const neddf_field_t* f, const neddf_field_state_t* st, const float* d_ray_dir,
+                                        const float* d_ray_orig, const float* d_dists, int64_t n_rays, int32_t n_edges,
+                                        int32_t sampling_type, float ray_radius, const float* d_save_pre,
+                                        const float* g_density, const float* g_color, const float* g_penalty,
+                                        float* d_post, float* d_gpre, float* d_ghead_da, float* d_ghead_col,
+                                        float* d_xes, float* d_xcol, void* stream) {
+  FieldParams p;
+  int32_t rc = fill_rays(f, st, p, d_ray_dir, d_ray_orig, d_dists, n_rays, n_edges, sampling_type, ray_radius,
+                         "neddf_field_backward");
+  if (rc != NEDDF_OK) return rc;
+  if (!d_save_pre || !g_density || !g_color || !d_post || !d_gpre || !d_ghead_da || !d_ghead_col || !d_xes || !d_xcol)
+    return fail(NEDDF_E_INVALID, "neddf_field_backward: NULL buffer");
+  BackwardIO io;
+  io.save_pre = d_save_pre;
+  io.g_density = g_density; io.g_color = g_color; io.g_penalty = g_penalty;
+  io.post = d_post; io.gpre = d_gpre; io.ghead_da = d_ghead_da; io.ghead_col = d_ghead_col;
+  io.xes = d_xes; io.xcol = d_xcol;
+  return launch_field_backward(f, p, io, (cudaStream_t)stream);
 }

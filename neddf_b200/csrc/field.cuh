@@ -63,6 +63,23 @@ struct FieldParams {
   float* color;
   float* penalty;
   float* aux_grad;
+  // training: pre-activations of every hidden layer, [n_hidden][n][4][256] (value row incl. bias,
+  // then the 3 Jacobian rows), written by the fp32 engine when non-null
+  float* save_pre;
+};
+
+// Buffers of the training backward (all device, fp32, row-major)
+struct BackwardIO {
+  const float* save_pre;    // [n_hidden][n][4][256] from the training forward
+  const float* g_density;   // [n]
+  const float* g_color;     // [n][3]
+  const float* g_penalty;   // [n] (may be null)
+  float* post;              // [n_hidden][n][4][256] post-activations (inputs of the next layer / heads)
+  float* gpre;              // [n_hidden][n][4][256] gradient w.r.t. the pre-activations
+  float* ghead_da;          // [n][4][2]  gradient w.r.t. (ddf_out, aux_out) value + Jacobian rows
+  float* ghead_col;         // [n][4][4]  gradient w.r.t. colour head outputs (3 used)
+  float* xes;               // [n][4][n_e0]        scaled position embedding (input of layer 0 / skip)
+  float* xcol;              // [n][4][off_h]       [E0 | D | n] (input part of colour layer 0)
 };
 
 }  // namespace neddf
@@ -78,6 +95,8 @@ struct neddf_field {
   float* d_w_head_da = nullptr;
   float* d_w_head_col = nullptr;
   float* d_b_head = nullptr;  // [8] head biases: ddf, aux, r, g, b
+  float* d_wt_hidden = nullptr;  // backward: transposed h-part of every hidden layer l >= 1, packed like w_hidden
+  int wt_chunks = 0;
   bool weights_set = false;
   // tensor-core engine storage (field_tc.cu)
   void* tc = nullptr;
@@ -85,6 +104,9 @@ struct neddf_field {
 
 namespace neddf {
 int32_t launch_field_fp32(const neddf_field* f, FieldParams& p, cudaStream_t s);
+int32_t launch_field_backward(const neddf_field* f, FieldParams& p, const BackwardIO& io, cudaStream_t s);
+int32_t pack_backward_weights(neddf_field* f, const float* const* d_w, cudaStream_t s);
+
 int32_t tc_pack_weights(neddf_field* f, const float* const* d_w, const float* const* d_b, cudaStream_t s);
 int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStream_t s);
 bool tc_supported(const neddf_field* f);

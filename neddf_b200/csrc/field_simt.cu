@@ -223,8 +223,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_simt_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float y, d1;
-        hidden_act<ACT>(acc[0][i] + __ldg(bias + (i >> 2) * 64 + (i & 3)), y, d1);
+        const float xpre = acc[0][i] + __ldg(bias + (i >> 2) * 64 + (i & 3));
+        hidden_act<ACT>(xpre, y, d1);
         const int ch = cg + 16 * i;
+        if (p.save_pre && valid) {  // training: keep the pre-activations for the backward kernel
+          float* dst = p.save_pre + (((size_t)l * p.n + my_n) * 4) * kWidth + ch;
+          dst[0] = xpre;
+          dst[kWidth] = acc[1][i];
+          dst[2 * kWidth] = acc[2][i];
+          dst[3 * kWidth] = acc[3][i];
+        }
         *reinterpret_cast<float4*>(&act[(size_t)(p.off_h + ch) * kPitch + 4 * s_slot]) =
             make_float4(y, d1 * acc[1][i], d1 * acc[2][i], d1 * acc[3][i]);
       }

@@ -39,6 +39,101 @@ class LinearGradLayer(nn.Module):
                                   "call NeDDF.forward instead")
 
 
+class _FieldTrainFn(torch.autograd.Function):
+    """Differentiable NeDDF.forward on rays + edge distances (training path, fp32 engine).
+
+    forward : neddf_field_forward_train - the fused fp32 megakernel, keeping every layer's
+              pre-activations.
+    backward: neddf_field_backward does all sample-local work (activation second derivatives, heads,
+              density, penalties, data-gradient GEMMs) and writes per-layer inputs X_l and
+              pre-activation gradients G_l; the weight gradients gW_l = X_l^T G_l are plain GEMMs over
+              all samples (cuBLAS through torch.matmul), bias gradients column sums.
+    Gradients flow to the module's parameters only (sample positions come from torch.rand / a
+    no_grad resampling in the reference, nerf_render.py:131-166).
+    """
+
+    @staticmethod
+    def forward(ctx, net, ray_dir, ray_orig, dists, sampling_type, ray_radius, *params):
+        B, S = dists.shape
+        n = B * S
+        device = dists.device
+        n_hidden = (net.ddf_layer_count - 1) + (net.col_layer_count - 1)
+        h = net._field(device)
+        st = net._state_struct()
+        save = torch.empty(n_hidden, n, 4, 256, device=device, dtype=torch.float32)
+        density = torch.empty(B, S, device=device, dtype=torch.float32)
+        color = torch.empty(B, S, 3, device=device, dtype=torch.float32)
+        penalty = torch.empty(B, S, device=device, dtype=torch.float32)
+        with torch.cuda.device(device):
+            L.check(L.lib().neddf_field_forward_train(
+                h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, S, L.SAMPLING_IDS[sampling_type],
+                float(ray_radius), L.ptr(density), L.ptr(color), L.ptr(penalty), L.ptr(save), L.stream_ptr(device)),
+                "field_forward_train")
+        ctx.net = net
+        ctx.meta = (sampling_type, float(ray_radius), (st.aux_grad_scale, st.distance_range_max, st.lowpass_alpha))
+        ctx.save_for_backward(ray_dir, ray_orig, dists, save)
+        return density, color, penalty
+
+    @staticmethod
+    def backward(ctx, g_density, g_color, g_penalty):
+        net = ctx.net
+        ray_dir, ray_orig, dists, save = ctx.saved_tensors
+        sampling_type, ray_radius, stv = ctx.meta
+        B, S = dists.shape
+        n = B * S
+        device = dists.device
+        n_ddf, n_col = net.ddf_layer_count - 1, net.col_layer_count - 1
+        n_hidden = n_ddf + n_col
+        n_e0 = 6 * net.embed_pos_rank
+        off_h = 6 * (net.embed_pos_rank + net.embed_dir_rank) + 3
+
+        def prep(g, shape):
+            if g is None:
+                return torch.zeros(shape, device=device, dtype=torch.float32)
+            return g.contiguous().to(torch.float32)
+
+        g_density = prep(g_density, (B, S))
+        g_color = prep(g_color, (B, S, 3))
+        g_penalty = prep(g_penalty, (B, S))
+        post = torch.empty(n_hidden, n, 4, 256, device=device, dtype=torch.float32)
+        gpre = torch.empty(n_hidden, n, 4, 256, device=device, dtype=torch.float32)
+        ghead_da = torch.empty(n, 4, 2, device=device, dtype=torch.float32)
+        ghead_col = torch.empty(n, 4, 4, device=device, dtype=torch.float32)
+        xes = torch.empty(n, 4, n_e0, device=device, dtype=torch.float32)
+        xcol = torch.empty(n, 4, off_h, device=device, dtype=torch.float32)
+        h = net._field(device)
+        st = L.FieldState(*stv)
+        with torch.cuda.device(device):
+            L.check(L.lib().neddf_field_backward(
+                h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, S, L.SAMPLING_IDS[sampling_type],
+                ray_radius, L.ptr(save), L.ptr(g_density), L.ptr(g_color), L.ptr(g_penalty), L.ptr(post), L.ptr(gpre),
+                L.ptr(ghead_da), L.ptr(ghead_col), L.ptr(xes), L.ptr(xcol), L.stream_ptr(device)), "field_backward")
+
+        # weight gradients: gW = X^T G over the 4N rows (linear.py:76-79), bias = sum over value rows
+        def wgrad(parts, G):
+            G2 = G.reshape(4 * n, -1)
+            return torch.cat([x.reshape(4 * n, -1).t() @ G2 for x in parts], 0)
+
+        grads = []
+        for l in range(n_hidden):
+            if l == 0:
+                parts = [xes]
+            elif l < n_ddf:
+                parts = ([xes] if (l - 1) in net.skips else []) + [post[l - 1]]
+            elif l == n_ddf:
+                parts = [xcol, post[n_ddf - 1]]
+            else:
+                parts = [post[l - 1]]
+            grads.append(wgrad(parts, gpre[l]))
+            grads.append(gpre[l][:, 0, :].sum(0))
+        g_da = wgrad([post[n_ddf - 1]], ghead_da)           # [256, 2]
+        b_da = ghead_da[:, 0, :].sum(0)
+        grads += [g_da[:, 0:1].contiguous(), b_da[0:1].contiguous(), g_da[:, 1:2].contiguous(), b_da[1:2].contiguous()]
+        g_c = wgrad([post[n_hidden - 1]], ghead_col)[:, :3]
+        grads += [g_c.contiguous(), ghead_col[:, 0, :3].sum(0)]
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
 class BaseNeuralField(nn.Module):
     """neddf/network/base_neuralfield.py:11-79."""
 
@@ -212,8 +307,8 @@ class NeDDF(BaseNeuralField):
     def _check_no_grad(self) -> None:
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "neddf_b200: the differentiable (training) path of the field kernel is not built yet; "
-                "call under torch.no_grad() / render_image. (Tracked in DESIGN.md, scope row a9.)")
+                "neddf_b200: NeDDF.forward(Sampling) has no differentiable path; training goes through "
+                "NeRFRender.render_rays (rays + edge distances).  Call this under torch.no_grad().")
 
     # ------------------------------------------------------------------------- forward --
     def forward(self, sampling: Sampling) -> Dict[str, Tensor]:
@@ -247,8 +342,15 @@ class NeDDF(BaseNeuralField):
     def forward_rays(self, ray_dir: Tensor, ray_orig: Tensor, dists: Tensor, sampling_type: str, ray_radius: float,
                      need_penalty: bool = True, need_aux: bool = True) -> Dict[str, Tensor]:
         """Same network with the sample geometry fused into the kernel prologue (no [N,3]
-        Sampling tensors in HBM).  Used by NeRFRender."""
-        self._check_no_grad()
+        Sampling tensors in HBM).  Used by NeRFRender.  Under autograd (training) it runs the
+        differentiable fp32 path (_FieldTrainFn) and returns density / color / fields_penalty."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            ray_dir = L.require_cuda_f32(ray_dir, "ray_dir")
+            ray_orig = L.require_cuda_f32(ray_orig, "ray_orig")
+            dists = L.require_cuda_f32(dists, "dists")
+            flat = [t for l in self._ordered_layers() for t in (l.weight, l.bias)]
+            d, c, pnl = _FieldTrainFn.apply(self, ray_dir, ray_orig, dists, sampling_type, ray_radius, *flat)
+            return {"density": d, "color": c, "fields_penalty": pnl}
         ray_dir = L.require_cuda_f32(ray_dir, "ray_dir")
         ray_orig = L.require_cuda_f32(ray_orig, "ray_orig")
         dists = L.require_cuda_f32(dists, "dists")

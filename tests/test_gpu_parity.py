@@ -273,7 +273,9 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         render.render_rays(c.t("uv"), cam)  # CPU uv
     with pytest.raises(NotImplementedError):
-        render.render_rays(c.t("uv").to(G.DEV), cam)  # grad enabled: training path not built yet
+        s_ = neddf_b200.Sampling(torch.zeros(1, 4, 3, device=G.DEV), torch.zeros(1, 4, 3, device=G.DEV),
+                                 torch.zeros(1, 4, 3, device=G.DEV))
+        render.network_fine(s_)  # NeDDF.forward(Sampling) under autograd: training goes through render_rays
     with pytest.raises(ValueError):
         with torch.no_grad():
             render.render_rays(c.t("uv").to(G.DEV), cam, uniforms=(torch.rand(3, 65), torch.rand(3, 129)))
@@ -482,3 +484,71 @@ def test_composite_backward_matches_autograd(name):
     assert nerr(cd.grad.cpu().numpy(), col.grad.numpy()) < 2e-5
     assert nerr(pd.grad.cpu().numpy(), pen.grad.numpy()) < 2e-5
     assert float(dd.grad[:, -1].abs().max()) == 0.0  # the closing edge receives no gradient
+
+
+@pytest.mark.parametrize("name", ["train", "bunny"])
+def test_field_backward_matches_autograd(name):
+    """Training path of the field (neddf_field_forward_train + neddf_field_backward + cuBLAS weight
+    gradients) against autograd through the oracle, for random upstream gradients of density,
+    colour and fields_penalty."""
+    G = _gpu()
+    c = Case(name)
+    render = G.build_render(c, "fp32")
+    net = render.network_fine
+    n_rays = 6
+    d, o = orc.make_rays(c.t("uv")[:n_rays], c.cam)
+    dists = c.t("dists_fine")[:n_rays, ::3].contiguous()
+    pos, dd, var = orc.make_samples(c.rc, d, o, dists)
+    g = torch.Generator().manual_seed(4)
+    B, S = dists.shape
+    gd, gc, gp = torch.randn(B, S, generator=g), torch.randn(B, S, 3, generator=g), torch.randn(B, S, generator=g)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in c.p_fine.items()}
+    ref = orc.field_forward(Pg, c.fc, c.st, pos, dd.contiguous(), var)
+    ((ref["density"] * gd).sum() + (ref["color"] * gc).sum() + (ref["fields_penalty"] * gp).sum()).backward()
+    out = net.forward_rays(d.contiguous().to(G.DEV), o.contiguous().to(G.DEV), dists.to(G.DEV), c.rc.sampling_type,
+                           render._ray_radius)
+    for k in ("density", "color", "fields_penalty"):
+        assert nerr(out[k].detach().cpu().numpy(), ref[k].detach().numpy()) < PARITY_TOL, k
+    loss = (out["density"] * gd.to(G.DEV)).sum() + (out["color"] * gc.to(G.DEV)).sum() + \
+        (out["fields_penalty"] * gp.to(G.DEV)).sum()
+    net.zero_grad()
+    loss.backward()
+    for k, v in Pg.items():
+        mod, attr = k.rsplit(".", 1)
+        obj = net
+        for part in mod.split("."):
+            obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+        got = getattr(obj, attr).grad
+        assert got is not None, k
+        assert nerr(got.cpu().numpy(), v.grad.numpy()) < 2e-3, k
+
+
+def test_render_rays_training_matches_reference_gradients():
+    """drums-config inner loop (forward + backward) on the golden training case: outputs and the
+    parameter gradients of the reference's own backward (hand-written autograd Functions,
+    run.py / nerf_trainer.py:108-122) for the recorded loss."""
+    G = _gpu()
+    c = Case("train")
+    render, cam = G.build_render(c, "auto"), G.build_camera(c)
+    out = render.render_rays(c.t("uv").to(G.DEV), cam, uniforms=(c.t("u_coarse").to(G.DEV), c.t("u_fine").to(G.DEV)))
+    for k, v in c.outputs().items():
+        tol = 1e-3 if k == "weight" else PARITY_TOL
+        assert nerr(out[k].detach().cpu().numpy(), v) < tol, k
+    loss = (out["color"].sum() + 0.1 * out["depth"].sum() + 0.05 * out["transmittance"].sum()
+            + 0.01 * out["fields_penalty"].sum() + 0.1 * out["color_coarse"].sum()
+            + 0.001 * out["fields_penalty_coarse"].sum())
+    assert abs(float(loss) - float(c.z["loss"])) < 1e-4 * abs(float(c.z["loss"]))
+    render.zero_grad()
+    loss.backward()
+    checked = 0
+    for name, p in render.named_parameters():
+        key = "grad_" + name
+        if key not in c.z:
+            key = "grad_" + name.replace("network_fine.", "network_coarse.")
+        ref = c.z[key]
+        g = p.grad.cpu().numpy()
+        if g.ndim == 2 and g.shape[1] > 3:
+            g = g[::8]
+        assert nerr(g, ref) < 2e-3, name
+        checked += 1
+    assert checked == 26
