@@ -193,6 +193,19 @@ int32_t neddf_field_backward(const neddf_field_t* f, const neddf_field_state_t* 
                              float* d_gpre, float* d_ghead_da, float* d_ghead_col, float* d_xes, float* d_xcol,
                              void* stream);
 
+/* The same training forward / backward on Sampling tensors pos/dir/var [n,3] (NeDDF.forward(sampling)
+ * under autograd).  The forward also returns distance and aux_grad; their gradients are not
+ * propagated (the reference's losses never consume them). */
+int32_t neddf_field_forward_train_samples(const neddf_field_t* f, const neddf_field_state_t* st,
+                                          const float* d_pos, const float* d_dir, const float* d_var, int64_t n,
+                                          float* d_distance, float* d_density, float* d_color, float* d_penalty,
+                                          float* d_aux_grad, float* d_save_pre, void* stream);
+int32_t neddf_field_backward_samples(const neddf_field_t* f, const neddf_field_state_t* st, const float* d_pos,
+                                     const float* d_dir, const float* d_var, int64_t n, const float* d_save_pre,
+                                     const float* g_density, const float* g_color, const float* g_penalty,
+                                     float* d_post, float* d_gpre, float* d_ghead_da, float* d_ghead_col,
+                                     float* d_xes, float* d_xcol, void* stream);
+
 /* BaseNeuralRender.integrate_volume_render (neddf/render/base_neural_render.py:117-172) plus
  * the penalty integration of render_rays (nerf_render.py:153-159).
  * in : dists[n_rays,n_edges], density[n_rays,n_edges], color[n_rays,n_edges,3],

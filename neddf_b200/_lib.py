@@ -63,6 +63,9 @@ _SIGNATURES = {
     "neddf_field_forward_train": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "neddf_field_backward": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P]),
+    "neddf_field_forward_train_samples": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "neddf_field_backward_samples": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P,
+                                            _P, _P, _P, _P]),
     "neddf_composite": (_I32, [_P, _P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P, _P]),
     "neddf_composite_backward": (_I32, [_P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "neddf_sample_pdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -415,3 +415,50 @@ extern "C" int32_t neddf_field_backward(const neddf_field_t* f, const neddf_fiel
   io.xes = d_xes; io.xcol = d_xcol;
   return launch_field_backward(f, p, io, (cudaStream_t)stream);
 }
+
+static int32_t fill_samples(const neddf_field* f, const neddf_field_state_t* st, FieldParams& p, const float* d_pos,
+                            const float* d_dir, const float* d_var, int64_t n, const char* who) {
+  if (!f) return fail(NEDDF_E_INVALID, std::string(who) + ": field is NULL");
+  if (!f->weights_set) return fail(NEDDF_E_INVALID, std::string(who) + ": weights were never set");
+  if (n <= 0) return fail(NEDDF_E_INVALID, std::string(who) + ": n <= 0");
+  if (!d_pos || !d_dir || !d_var) return fail(NEDDF_E_INVALID, std::string(who) + ": NULL input pointer");
+  p = f->proto;
+  int32_t rc = fill_state(f, st, p);
+  if (rc != NEDDF_OK) return rc;
+  p.pos = d_pos; p.dir = d_dir; p.var = d_var;
+  p.n = n;
+  return NEDDF_OK;
+}
+
+extern "C" int32_t neddf_field_forward_train_samples(const neddf_field_t* f, const neddf_field_state_t* st,
+                                                     const float* d_pos, const float* d_dir, const float* d_var,
+                                                     int64_t n, float* d_distance, float* d_density, float* d_color,
+                                                     float* d_penalty, float* d_aux_grad, float* d_save_pre,
+                                                     void* stream) {
+  FieldParams p;
+  int32_t rc = fill_samples(f, st, p, d_pos, d_dir, d_var, n, "neddf_field_forward_train_samples");
+  if (rc != NEDDF_OK) return rc;
+  if (!d_save_pre) return fail(NEDDF_E_INVALID, "neddf_field_forward_train_samples: d_save_pre is NULL");
+  p.distance = d_distance; p.density = d_density; p.color = d_color; p.penalty = d_penalty; p.aux_grad = d_aux_grad;
+  p.save_pre = d_save_pre;
+  return launch_field_fp32(f, p, (cudaStream_t)stream);
+}
+
+extern "C" int32_t neddf_field_backward_samples(const neddf_field_t* f, const neddf_field_state_t* st,
+                                                const float* d_pos, const float* d_dir, const float* d_var, int64_t n,
+                                                const float* d_save_pre, const float* g_density, const float* g_color,
+                                                const float* g_penalty, float* d_post, float* d_gpre,
+                                                float* d_ghead_da, float* d_ghead_col, float* d_xes, float* d_xcol,
+                                                void* stream) {
+  FieldParams p;
+  int32_t rc = fill_samples(f, st, p, d_pos, d_dir, d_var, n, "neddf_field_backward_samples");
+  if (rc != NEDDF_OK) return rc;
+  if (!d_save_pre || !g_density || !g_color || !d_post || !d_gpre || !d_ghead_da || !d_ghead_col || !d_xes || !d_xcol)
+    return fail(NEDDF_E_INVALID, "neddf_field_backward_samples: NULL buffer");
+  BackwardIO io;
+  io.save_pre = d_save_pre;
+  io.g_density = g_density; io.g_color = g_color; io.g_penalty = g_penalty;
+  io.post = d_post; io.gpre = d_gpre; io.ghead_da = d_ghead_da; io.ghead_col = d_ghead_col;
+  io.xes = d_xes; io.xcol = d_xcol;
+  return launch_field_backward(f, p, io, (cudaStream_t)stream);
+}

@@ -53,10 +53,13 @@ class _FieldTrainFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, net, ray_dir, ray_orig, dists, sampling_type, ray_radius, *params):
-        B, S = dists.shape
+    def forward(ctx, net, a, b, c, sampling_type, ray_radius, *params):
+        """(a, b, c) = (ray_dir[B,3], ray_orig[B,3], dists[B,S]) with a sampling type, or the Sampling
+        tensors (pos, dir, var)[B,S,3] when sampling_type is None."""
+        from_rays = sampling_type is not None
+        B, S = (c.shape if from_rays else a.shape[:2])
         n = B * S
-        device = dists.device
+        device = a.device
         n_hidden = (net.ddf_layer_count - 1) + (net.col_layer_count - 1)
         h = net._field(device)
         st = net._state_struct()
@@ -64,24 +67,34 @@ class _FieldTrainFn(torch.autograd.Function):
         density = torch.empty(B, S, device=device, dtype=torch.float32)
         color = torch.empty(B, S, 3, device=device, dtype=torch.float32)
         penalty = torch.empty(B, S, device=device, dtype=torch.float32)
+        distance = torch.empty(B, S, device=device, dtype=torch.float32) if not from_rays else None
+        aux = torch.empty(B, S, device=device, dtype=torch.float32) if not from_rays else None
         with torch.cuda.device(device):
-            L.check(L.lib().neddf_field_forward_train(
-                h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, S, L.SAMPLING_IDS[sampling_type],
-                float(ray_radius), L.ptr(density), L.ptr(color), L.ptr(penalty), L.ptr(save), L.stream_ptr(device)),
-                "field_forward_train")
+            if from_rays:
+                L.check(L.lib().neddf_field_forward_train(
+                    h, C.byref(st), L.ptr(a), L.ptr(b), L.ptr(c), B, S, L.SAMPLING_IDS[sampling_type],
+                    float(ray_radius), L.ptr(density), L.ptr(color), L.ptr(penalty), L.ptr(save), L.stream_ptr(device)),
+                    "field_forward_train")
+            else:
+                L.check(L.lib().neddf_field_forward_train_samples(
+                    h, C.byref(st), L.ptr(a), L.ptr(b), L.ptr(c), n, L.ptr(distance), L.ptr(density), L.ptr(color),
+                    L.ptr(penalty), L.ptr(aux), L.ptr(save), L.stream_ptr(device)), "field_forward_train_samples")
         ctx.net = net
-        ctx.meta = (sampling_type, float(ray_radius), (st.aux_grad_scale, st.distance_range_max, st.lowpass_alpha))
-        ctx.save_for_backward(ray_dir, ray_orig, dists, save)
-        return density, color, penalty
+        ctx.meta = (sampling_type, float(ray_radius), (st.aux_grad_scale, st.distance_range_max, st.lowpass_alpha), (B, S))
+        ctx.save_for_backward(a, b, c, save)
+        if from_rays:
+            return density, color, penalty
+        ctx.mark_non_differentiable(distance, aux)
+        return density, color, penalty, distance, aux
 
     @staticmethod
-    def backward(ctx, g_density, g_color, g_penalty):
+    def backward(ctx, g_density, g_color, g_penalty, *unused):
         net = ctx.net
-        ray_dir, ray_orig, dists, save = ctx.saved_tensors
-        sampling_type, ray_radius, stv = ctx.meta
-        B, S = dists.shape
+        ga, gb_, gc_, save = ctx.saved_tensors
+        sampling_type, ray_radius, stv, (B, S) = ctx.meta
+        from_rays = sampling_type is not None
         n = B * S
-        device = dists.device
+        device = ga.device
         n_ddf, n_col = net.ddf_layer_count - 1, net.col_layer_count - 1
         n_hidden = n_ddf + n_col
         n_e0 = 6 * net.embed_pos_rank
@@ -104,10 +117,17 @@ class _FieldTrainFn(torch.autograd.Function):
         h = net._field(device)
         st = L.FieldState(*stv)
         with torch.cuda.device(device):
-            L.check(L.lib().neddf_field_backward(
-                h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, S, L.SAMPLING_IDS[sampling_type],
-                ray_radius, L.ptr(save), L.ptr(g_density), L.ptr(g_color), L.ptr(g_penalty), L.ptr(post), L.ptr(gpre),
-                L.ptr(ghead_da), L.ptr(ghead_col), L.ptr(xes), L.ptr(xcol), L.stream_ptr(device)), "field_backward")
+            if from_rays:
+                L.check(L.lib().neddf_field_backward(
+                    h, C.byref(st), L.ptr(ga), L.ptr(gb_), L.ptr(gc_), B, S, L.SAMPLING_IDS[sampling_type],
+                    ray_radius, L.ptr(save), L.ptr(g_density), L.ptr(g_color), L.ptr(g_penalty), L.ptr(post),
+                    L.ptr(gpre), L.ptr(ghead_da), L.ptr(ghead_col), L.ptr(xes), L.ptr(xcol), L.stream_ptr(device)),
+                    "field_backward")
+            else:
+                L.check(L.lib().neddf_field_backward_samples(
+                    h, C.byref(st), L.ptr(ga), L.ptr(gb_), L.ptr(gc_), n, L.ptr(save), L.ptr(g_density),
+                    L.ptr(g_color), L.ptr(g_penalty), L.ptr(post), L.ptr(gpre), L.ptr(ghead_da), L.ptr(ghead_col),
+                    L.ptr(xes), L.ptr(xcol), L.stream_ptr(device)), "field_backward_samples")
 
         # weight gradients: gW = X^T G over the 4N rows (linear.py:76-79), bias = sum over value rows
         def wgrad(parts, G):
@@ -304,18 +324,21 @@ class NeDDF(BaseNeuralField):
         self._packed_key = None  # .to()/.cuda() replaced the parameter storage
         return r
 
-    def _check_no_grad(self) -> None:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "neddf_b200: NeDDF.forward(Sampling) has no differentiable path; training goes through "
-                "NeRFRender.render_rays (rays + edge distances).  Call this under torch.no_grad().")
-
     # ------------------------------------------------------------------------- forward --
     def forward(self, sampling: Sampling) -> Dict[str, Tensor]:
         """NeDDF.forward (neddf.py:162-309): Sampling[B,S,3] -> distance, density, color,
-        fields_penalty, aux_grad."""
-        self._check_no_grad()
+        fields_penalty, aux_grad.  Under autograd: the differentiable fp32 path (gradients to the
+        parameters through density / color / fields_penalty; distance and aux_grad are returned
+        without a graph - no loss of the reference consumes them)."""
         pos = sampling.sample_pos
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            B, S = pos.shape[0], pos.shape[1]
+            p3 = L.require_cuda_f32(pos.reshape(B, S, 3), "sample_pos")
+            d3 = L.require_cuda_f32(sampling.sample_dir.reshape(B, S, 3), "sample_dir")
+            v3 = L.require_cuda_f32(sampling.diag_variance.reshape(B, S, 3), "diag_variance")
+            flat = [t for l in self._ordered_layers() for t in (l.weight, l.bias)]
+            d, c, pnl, dist, aux = _FieldTrainFn.apply(self, p3, d3, v3, None, 0.0, *flat)
+            return {"distance": dist, "density": d, "color": c, "fields_penalty": pnl, "aux_grad": aux}
         B, S = pos.shape[0], pos.shape[1]
         device = pos.device
         # reshape, not view: accept the expanded tensors the reference's point sampler returns

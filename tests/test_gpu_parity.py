@@ -272,10 +272,6 @@ def test_errors_are_loud():
     render, cam = G.build_render(c), G.build_camera(c)
     with pytest.raises(RuntimeError):
         render.render_rays(c.t("uv"), cam)  # CPU uv
-    with pytest.raises(NotImplementedError):
-        s_ = neddf_b200.Sampling(torch.zeros(1, 4, 3, device=G.DEV), torch.zeros(1, 4, 3, device=G.DEV),
-                                 torch.zeros(1, 4, 3, device=G.DEV))
-        render.network_fine(s_)  # NeDDF.forward(Sampling) under autograd: training goes through render_rays
     with pytest.raises(ValueError):
         with torch.no_grad():
             render.render_rays(c.t("uv").to(G.DEV), cam, uniforms=(torch.rand(3, 65), torch.rand(3, 129)))
@@ -552,3 +548,37 @@ def test_render_rays_training_matches_reference_gradients():
         assert nerr(g, ref) < 2e-3, name
         checked += 1
     assert checked == 26
+
+
+def test_network_forward_sampling_is_differentiable():
+    """NeDDF.forward(Sampling) under autograd (the reference's trainer test runs exactly this through
+    render_rays; direct callers get the same differentiable path): values and parameter gradients
+    against autograd through the oracle."""
+    G = _gpu()
+    import neddf_b200
+    c = Case("default")
+    render = G.build_render(c, "auto")
+    net = render.network_fine
+    g = torch.Generator().manual_seed(11)
+    B, S = 3, 21
+    pos = (torch.rand(B, S, 3, generator=g) - 0.5) * 2.0
+    dd = torch.nn.functional.normalize(torch.randn(B, S, 3, generator=g), dim=-1)
+    var = torch.rand(B, S, 3, generator=g) * 1e-3
+    gd, gc, gp = torch.randn(B, S, generator=g), torch.randn(B, S, 3, generator=g), torch.randn(B, S, generator=g)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in c.p_fine.items()}
+    ref = orc.field_forward(Pg, c.fc, c.st, pos, dd, var)
+    ((ref["density"] * gd).sum() + (ref["color"] * gc).sum() + (ref["fields_penalty"] * gp).sum()).backward()
+    out = net(neddf_b200.Sampling(pos.to(G.DEV), dd.to(G.DEV), var.to(G.DEV)))
+    assert set(out) == {"distance", "density", "color", "fields_penalty", "aux_grad"}
+    for k in out:
+        assert nerr(out[k].detach().cpu().numpy(), ref[k].detach().numpy()) < PARITY_TOL, k
+    assert out["density"].requires_grad and not out["distance"].requires_grad
+    net.zero_grad()
+    ((out["density"] * gd.to(G.DEV)).sum() + (out["color"] * gc.to(G.DEV)).sum() + (out["fields_penalty"] * gp.to(G.DEV)).sum()).backward()
+    for k in ("layers_ddf.0.weight", "layers_ddf.5.weight", "layers_col.0.weight", "layer_ddf_out.weight",
+              "layer_aux_out.bias", "layer_col_out.weight", "layers_ddf.6.bias"):
+        mod, attr = k.rsplit(".", 1)
+        obj = net
+        for part in mod.split("."):
+            obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+        assert nerr(getattr(obj, attr).grad.cpu().numpy(), Pg[k].grad.numpy()) < 2e-3, k
