@@ -166,7 +166,7 @@ int32_t neddf_field_forward_rays(const neddf_field_t* f, const neddf_field_state
                                  float* d_density, float* d_color, float* d_penalty,
                                  float* d_aux_grad, int32_t flags, int32_t engine, void* stream);
 
-/* Training forward (fp32 engine) of NeDDF.forward on rays + edge distances: like
+/* Training forward of NeDDF.forward on rays + edge distances (tensor-core engine when available): like
  * neddf_field_forward_rays with NEDDF_OUT_FULL, and additionally keeps the pre-activations of every
  * hidden layer in d_save_pre [n_hidden][n][4][256] (n = n_rays*n_edges; value row incl. bias, then the
  * three Jacobian rows) for neddf_field_backward. */

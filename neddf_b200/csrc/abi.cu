@@ -393,7 +393,9 @@ extern "C" int32_t neddf_field_forward_train(const neddf_field_t* f, const neddf
   if (!d_save_pre) return fail(NEDDF_E_INVALID, "neddf_field_forward_train: d_save_pre is NULL");
   p.density = d_density; p.color = d_color; p.penalty = d_penalty;
   p.save_pre = d_save_pre;
-  return launch_field_fp32(f, p, (cudaStream_t)stream);
+  // the tensor-core engine produces the same saved pre-activations (to ~1e-5); the backward itself
+  // is the fp32 kernel either way
+  return dispatch(f, p, NEDDF_OUT_FULL, NEDDF_ENGINE_AUTO, (cudaStream_t)stream);
 }
 
 extern "C" int32_t neddf_field_backward(const neddf_field_t* f, const neddf_field_state_t* st, const float* d_ray_dir,
@@ -441,7 +443,7 @@ extern "C" int32_t neddf_field_forward_train_samples(const neddf_field_t* f, con
   if (!d_save_pre) return fail(NEDDF_E_INVALID, "neddf_field_forward_train_samples: d_save_pre is NULL");
   p.distance = d_distance; p.density = d_density; p.color = d_color; p.penalty = d_penalty; p.aux_grad = d_aux_grad;
   p.save_pre = d_save_pre;
-  return launch_field_fp32(f, p, (cudaStream_t)stream);
+  return dispatch(f, p, NEDDF_OUT_FULL, NEDDF_ENGINE_AUTO, (cudaStream_t)stream);
 }
 
 extern "C" int32_t neddf_field_backward_samples(const neddf_field_t* f, const neddf_field_state_t* st,

@@ -671,6 +671,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             const int s0 = 16 * shalf + 8 * blk;
             float x[8], d1[8];
             tmem_ld8(tbase + s0, x);
+            // training: keep the pre-activations [layer][sample][row type][channel] for the backward
+            float* save = nullptr;
+            if (p.save_pre) save = p.save_pre + (((size_t)st.bias_off / kWidth * p.n + (n0 + s0)) * 4) * kWidth + ch;
+            if (save) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (n0 + s0 + i < p.n) save[(size_t)i * 4 * kWidth] = x[i] + bias;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) tc_hidden_act<ACT>(x[i] + bias, x[i], d1[i]);
             uint32_t h[4], l[4];
@@ -684,6 +692,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
               for (int j = 1; j < 4; ++j) {  // Jacobian rows: G = f'(x) J (tanh_exp.py:47-48)
                 float g[8];
                 tmem_ld8(tbase + 32 * j + s0, g);
+                if (save) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (n0 + s0 + i < p.n) save[((size_t)i * 4 + j) * kWidth] = g[i];
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) split2(d1[2 * i] * g[2 * i], d1[2 * i + 1] * g[2 * i + 1], h[i], l[i], bad);
                 off += 4 * (kHK * 16);
