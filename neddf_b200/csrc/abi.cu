@@ -143,6 +143,8 @@ extern "C" int32_t neddf_field_layer_shapes(const neddf_field_config_t* cfg, int
   return (int32_t)in.size();
 }
 
+extern "C" int32_t neddf_field_destroy(neddf_field_t* f);
+
 extern "C" int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_field_t** out) {
   if (!out) return fail(NEDDF_E_INVALID, "neddf_field_create: out is NULL");
   *out = nullptr;
@@ -151,7 +153,10 @@ extern "C" int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_fie
   neddf_field* f = new (std::nothrow) neddf_field();
   if (!f) return fail(NEDDF_E_INVALID, "out of host memory");
   f->cfg = *cfg;
-  NEDDF_CUDA_CHECK(cudaGetDevice(&f->device));
+  if (cudaGetDevice(&f->device) != cudaSuccess) {
+    delete f;
+    return fail(NEDDF_E_CUDA, "neddf_field_create: no CUDA device");
+  }
   f->n_ddf = cfg->ddf_layer_count - 1;
   f->n_col = cfg->col_layer_count - 1;
   layer_shapes(*cfg, f->shape_in, f->shape_out);
@@ -200,11 +205,17 @@ extern "C" int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_fie
   }
   p.chunks_per_tile = rows / kChunkRows;
 
-  NEDDF_CUDA_CHECK(cudaMalloc(&f->d_w_hidden, (size_t)rows * kWidth * sizeof(float)));
-  NEDDF_CUDA_CHECK(cudaMalloc(&f->d_b_hidden, (size_t)n_hidden * kWidth * sizeof(float)));
-  NEDDF_CUDA_CHECK(cudaMalloc(&f->d_w_head_da, kWidth * 2 * sizeof(float)));
-  NEDDF_CUDA_CHECK(cudaMalloc(&f->d_w_head_col, kWidth * 4 * sizeof(float)));
-  NEDDF_CUDA_CHECK(cudaMalloc(&f->d_b_head, 8 * sizeof(float)));
+  {
+    cudaError_t e = cudaMalloc(&f->d_w_hidden, (size_t)rows * kWidth * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_b_hidden, (size_t)n_hidden * kWidth * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_w_head_da, kWidth * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_w_head_col, kWidth * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_b_head, 8 * sizeof(float));
+    if (e != cudaSuccess) {
+      neddf_field_destroy(f);  // frees whatever was allocated
+      return fail(NEDDF_E_CUDA, std::string("neddf_field_create: cudaMalloc: ") + cudaGetErrorString(e));
+    }
+  }
   p.w_hidden = f->d_w_hidden;
   p.b_hidden = f->d_b_hidden;
   p.w_head_da = f->d_w_head_da;
