@@ -65,6 +65,7 @@ constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;          // warp 16
 constexpr int kLoadWarps = 8;                // warps 17-24: lane quarter w%4, chunk parity (w-17)/4
+constexpr int kLoadPerQuarter = kLoadWarps / 4;  // loader warps per TMEM lane quarter, taking chunks round-robin
 constexpr int kThreads = kEpiThreads + 32 + kLoadWarps * 32;
 constexpr uint32_t kACol = 256;              // first TMEM column of the weight ring
 constexpr int kMaxSteps = kMaxHidden + 2;
@@ -115,6 +116,8 @@ struct TcParams {
   int* status;
   int head_da_step;     // index of the distance/aux heads step
   int eval;             // 1 = images only: colour trunk on value rows (N = 32), no penalty / colour Jacobian
+  int debug;            // profiling aid (NEDDF_TC_DEBUG): 1 = skip the MMAs, 2 = loaders skip the L2 reads,
+                        // 4 = loaders skip the TMEM stores, 8 = epilogue skips the hidden-layer math; results are garbage
   long long* timeline;  // optional: CTA 0 writes 6 values per step (profiling aid)
   int timeline_cap;
 };
@@ -213,6 +216,26 @@ __device__ __forceinline__ void mma_f16_ts_elect(uint32_t d_tmem, uint32_t a_tme
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
       "}\n" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// One weight chunk: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (A_hi at TMEM columns a..a+7, A_lo at a+8..),
+// then tcgen05.commit to `bar` (shared-memory address) - one elected lane, one asm block.
+__device__ __forceinline__ void chunk_mma_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo,
+                                                uint32_t idesc, uint32_t accumulate, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, t;\n"
+      ".reg .b32 alo;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "setp.ne.b32 t, %8, 0;\n"
+      "add.u32 alo, %1, 8;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %4, {%7, %7, %7, %7}, p;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [alo], %2, %4, {%7, %7, %7, %7}, t;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %4, {%7, %7, %7, %7}, t;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(bar), "r"(0u), "r"(1u)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
@@ -485,9 +508,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     for (int i = 0; i < kDepth; ++i) {
       if (gf < total_chunks) {
         fetch(i, fidx);
-        fidx += 2;
+        fidx += kLoadPerQuarter;
         if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
-        gf += 2;
+        gf += kLoadPerQuarter;
       }
     }
     int stage = cpar;
@@ -503,19 +526,21 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           const uint32_t ta = tmem + lane_addr + kACol + stage * 16;
           const uint32_t w0[8] = {r[i][0].x, r[i][0].y, r[i][0].z, r[i][0].w, r[i][1].x, r[i][1].y, r[i][1].z, r[i][1].w};
           const uint32_t w1[8] = {r[i][2].x, r[i][2].y, r[i][2].z, r[i][2].w, r[i][3].x, r[i][3].y, r[i][3].z, r[i][3].w};
-          tmem_st8(ta, w0);
-          tmem_st8(ta + 8, w1);
-          if (gf < total_chunks) {  // refill this register slot (the scoreboard orders it after the stores read it)
+          if (!(P.debug & 4)) {
+            tmem_st8(ta, w0);
+            tmem_st8(ta + 8, w1);
+          }
+          if (gf < total_chunks && !(P.debug & 2)) {  // refill this register slot (the scoreboard orders it after the stores read it)
             fetch(i, fidx);
-            fidx += 2;
+            fidx += kLoadPerQuarter;
             if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
-            gf += 2;
+            gf += kLoadPerQuarter;
           }
           tmem_st_wait();
           tc_fence_before();
           if (lane == 0) mbar_arrive(&sc->a_full[stage]);
-          g += 2;
-          stage += 2;
+          g += kLoadPerQuarter;
+          stage += kLoadPerQuarter;
           if (stage >= kARing) {
             stage -= kARing;
             if (first_pass) first_pass = false;
@@ -541,7 +566,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         mbar_wait(&sc->act_ready[0], act_phase);
         if (st.kind != kStepHidden || si == 0) mbar_wait(&sc->act_ready[1], act_phase);
         tc_fence_after();
-        long long waited = 0;
         if (stamp) P.timeline[6 * tl + 0] = clock64();
         if (st.kind == kStepHidden) {
           // Per (K-step, channel half) one weight chunk in tensor memory and three MMAs
@@ -555,25 +579,31 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           // images only: the colour trunk (every hidden step after the distance heads) needs no
           // Jacobian rows - the value rows are rows 0..31 of the same operands
           const uint32_t idesc = (P.eval && si > P.head_da_step) ? kIdescHiddenValue : kIdescHidden;
-          auto issue = [&](int half, int ks_begin, int ks_end) {
-            const uint32_t d = tmem + half * kRows;
-            for (int ks = ks_begin; ks < ks_end; ++ks) {
-              const uint64_t off = (ks < nA) ? (uint64_t)(ks * 16) : (uint64_t)((ks - nA) * 16);
-              const uint64_t db_hi = ((ks < nA) ? dba_hi : dbh_hi) + off, db_lo = ((ks < nA) ? dba_lo : dbh_lo) + off;
-              const long long w0 = stamp ? clock64() : 0;
+          // One asm block per chunk (a single elect, three MMAs, the commit that frees the ring
+          // stage) and no per-iteration selects: the issuing warp shares its scheduler with six other
+          // warps, and every instruction between two chunks is tensor-core idle time once the MMA
+          // queue runs dry (tools/timeline.py, debug modes).
+          auto run = [&](uint32_t d, uint64_t db_hi, uint64_t db_lo, int n, uint32_t& acc) {
+            for (int i = 0; i < n; ++i) {
               mbar_wait(&sc->a_full[stage], full_par);
-              if (stamp) waited += clock64() - w0;
               tc_fence_after();
-              const uint32_t a = tmem + kACol + stage * 16;
-              mma_f16_ts_elect(d, a, db_hi, idesc, ks > 0);
-              mma_f16_ts_elect(d, a + 8, db_hi, idesc, 1);
-              mma_f16_ts_elect(d, a, db_lo, idesc, 1);
-              mma_commit_elect(&sc->a_empty[stage]);
+              chunk_mma_elect(d, tmem + kACol + stage * 16, db_hi, db_lo, idesc, acc, smem_u32(&sc->a_empty[stage]));
+              acc = 1;
+              db_hi += 16;  // 16 K = 256 bytes in descriptor units
+              db_lo += 16;
               if (++stage == kARing) {
                 stage = 0;
                 full_par ^= 1;
               }
             }
+          };
+          auto issue = [&](int half, int ks_begin, int ks_end) {
+            const uint32_t d = tmem + half * kRows;
+            uint32_t acc = ks_begin > 0;
+            const int a_end = ks_end < nA ? ks_end : nA;
+            if (ks_begin < a_end) run(d, dba_hi + ks_begin * 16, dba_lo + ks_begin * 16, a_end - ks_begin, acc);
+            const int h_begin = ks_begin > nA ? ks_begin : nA;
+            if (h_begin < ks_end) run(d, dbh_hi + (h_begin - nA) * 16, dbh_lo + (h_begin - nA) * 16, ks_end - h_begin, acc);
           };
           issue(0, 0, n0);
           if (si != 0) {  // accumulator 1 free, H[k >= 128] ready
@@ -603,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         act_phase ^= 1;
         if (stamp) {
           P.timeline[6 * tl + 1] = clock64();
-          P.timeline[6 * tl + 4] = waited;
+          P.timeline[6 * tl + 4] = 0;
         }
       }
     }
@@ -667,7 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           const uint32_t tbase = tmem + lane_addr + half * kRows;
           const bool value_only = P.eval && si > P.head_da_step;
 #pragma unroll 1
-          for (int blk = 0; blk < 2; ++blk) {  // 8 samples = one 16-byte row group per row type
+          for (int blk = (P.debug & 8) ? 2 : 0; blk < 2; ++blk) {  // 8 samples = one 16-byte row group per row type
             const int s0 = 16 * shalf + 8 * blk;
             float x[8], d1[8];
             tmem_ld8(tbase + s0, x);
@@ -1218,6 +1248,8 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
   P.status = S->d_status;
   P.eval = (flags == NEDDF_OUT_EVAL && p.penalty == nullptr) ? 1 : 0;
   P.head_da_step = S->head_da_step;
+  P.debug = 0;
+  if (const char* e = std::getenv("NEDDF_TC_DEBUG")) P.debug = std::atoi(e);
   P.timeline = S->timeline;
   P.timeline_cap = S->timeline_cap;
   int64_t n_tiles = (p.n + tc::kTileS - 1) / tc::kTileS;
