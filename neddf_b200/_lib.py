@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneddf_b200.so")
+# NEDDF_B200_LIB selects another build of the same ABI (tuning variants, tools/build_variant.py)
+LIB_PATH = os.environ.get("NEDDF_B200_LIB") or os.path.join(_HERE, "libneddf_b200.so")
 
 MAX_SKIPS = 8
 N_PENALTY = 6

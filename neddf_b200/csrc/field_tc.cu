@@ -64,7 +64,13 @@ constexpr int kARing = 16;          // weight chunks resident in tensor memory (
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;          // warp 16
-constexpr int kLoadWarps = 8;                // warps 17-24: lane quarter w%4, chunk parity (w-17)/4
+#ifndef NEDDF_TC_LOAD_WARPS
+#define NEDDF_TC_LOAD_WARPS 8   // tuning knobs for experiments (tools/build_variant.py); the shipped values
+#endif
+#ifndef NEDDF_TC_LOAD_DEPTH
+#define NEDDF_TC_LOAD_DEPTH 3   // are the measured best (profiles/r01_summary.md)
+#endif
+constexpr int kLoadWarps = NEDDF_TC_LOAD_WARPS;               // warps 17-24: lane quarter w%4, chunk parity (w-17)/4
 constexpr int kLoadPerQuarter = kLoadWarps / 4;  // loader warps per TMEM lane quarter, taking chunks round-robin
 constexpr int kThreads = kEpiThreads + 32 + kLoadWarps * 32;
 constexpr uint32_t kACol = 256;              // first TMEM column of the weight ring
@@ -242,6 +248,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t a[8], const uint32_t b[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]),
+      "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     const int cpar = (warp - kMmaWarp - 1) >> 2;  // this warp loads chunks g with (g & 1) == cpar
     const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
     const uint4* base = reinterpret_cast<const uint4*>(P.w_tc) + (size_t)(32 * quarter + lane) * 4;
-    constexpr int kDepth = 3;  // own chunks in flight in registers (= 6 chunks ahead of the MMA warp)
+    constexpr int kDepth = NEDDF_TC_LOAD_DEPTH;  // own chunks in flight in registers (= 6 chunks ahead of the MMA warp)
     uint4 r[kDepth][4];
     auto fetch = [&](int slot, int chunk) {
       const uint4* src = base + (size_t)chunk * (kChunkBytes / 16);
@@ -527,8 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           const uint32_t w0[8] = {r[i][0].x, r[i][0].y, r[i][0].z, r[i][0].w, r[i][1].x, r[i][1].y, r[i][1].z, r[i][1].w};
           const uint32_t w1[8] = {r[i][2].x, r[i][2].y, r[i][2].z, r[i][2].w, r[i][3].x, r[i][3].y, r[i][3].z, r[i][3].w};
           if (!(P.debug & 4)) {
-            tmem_st8(ta, w0);
-            tmem_st8(ta + 8, w1);
+            tmem_st16(ta, w0, w1);  // 8 hi words | 8 lo words of this lane's row
           }
           if (gf < total_chunks && !(P.debug & 2)) {  // refill this register slot (the scoreboard orders it after the stores read it)
             fetch(i, fidx);
