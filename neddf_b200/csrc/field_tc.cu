@@ -48,6 +48,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -1292,7 +1293,14 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
   P.eval = (flags == NEDDF_OUT_EVAL && p.penalty == nullptr) ? 1 : 0;
   P.head_da_step = S->head_da_step;
   P.debug = 0;
-  if (const char* e = std::getenv("NEDDF_TC_DEBUG")) P.debug = std::atoi(e);
+  if (const char* e = std::getenv("NEDDF_TC_DEBUG")) {
+    P.debug = std::atoi(e);
+    static bool warned = false;
+    if (P.debug && !warned) {
+      warned = true;
+      std::fprintf(stderr, "neddf_b200: NEDDF_TC_DEBUG=%d switches kernel stages off - timing only, results are garbage\n", P.debug);
+    }
+  }
   P.timeline = S->timeline;
   P.timeline_cap = S->timeline_cap;
   int64_t n_tiles = (p.n + tc::kTileS - 1) / tc::kTileS;
