@@ -245,30 +245,6 @@ __device__ __forceinline__ void chunk_mma_elect(uint32_t d_tmem, uint32_t a_tmem
       "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(bar), "r"(0u), "r"(1u)
       : "memory");
 }
-#ifdef NEDDF_TC_ISSUE_V2
-// Experimental (not validated on hardware yet, build with tools/build_variant.py v2 -DNEDDF_TC_ISSUE_V2):
-// same chunk, but the instruction descriptor is an immediate and the (all-zero) disable-output-lane
-// vector is omitted, which removes 6 of the R2UR.BROADCASTs ptxas emits per chunk.
-template <uint32_t IDESC>
-__device__ __forceinline__ void chunk_mma_elect_v2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo,
-                                                   uint32_t accumulate, uint32_t bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q, t;\n"
-      ".reg .b32 alo;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "setp.eq.b32 t, %5, %5;\n"
-      "add.u32 alo, %1, 8;\n"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %4, p;\n"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [alo], %2, %4, t;\n"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %4, t;\n"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_hi), "l"(b_lo), "n"(IDESC), "r"(accumulate), "r"(bar)
-      : "memory");
-}
-#endif
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -624,14 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             for (int i = 0; i < n; ++i) {
               mbar_wait(&sc->a_full[stage], full_par);
               tc_fence_after();
-#ifdef NEDDF_TC_ISSUE_V2
-              if (idesc == kIdescHidden)
-                chunk_mma_elect_v2<kIdescHidden>(d, tmem + kACol + stage * 16, db_hi, db_lo, acc, smem_u32(&sc->a_empty[stage]));
-              else
-                chunk_mma_elect_v2<kIdescHiddenValue>(d, tmem + kACol + stage * 16, db_hi, db_lo, acc, smem_u32(&sc->a_empty[stage]));
-#else
               chunk_mma_elect(d, tmem + kACol + stage * 16, db_hi, db_lo, idesc, acc, smem_u32(&sc->a_empty[stage]));
-#endif
               acc = 1;
               db_hi += 16;  // 16 K = 256 bytes in descriptor units
               db_lo += 16;
