@@ -14,7 +14,9 @@ or, without touching any file of the reference:
 import importlib
 
 
-def install() -> None:
+def install(patch_trainer: bool = False) -> None:
+    """Rebind the reference's render / network classes; with ``patch_trainer`` also replace
+    ``BaseTrainer.construct_ground_truth`` by the vectorised gather of ``neddf_b200.trainer_glue``."""
     import neddf_b200
 
     ref_render = importlib.import_module("neddf.render")
@@ -27,3 +29,8 @@ def install() -> None:
             setattr(importlib.import_module(mod), name, obj)
         except Exception:
             pass
+    if patch_trainer:
+        from neddf_b200 import trainer_glue
+
+        base_trainer = importlib.import_module("neddf.trainer.base_trainer")
+        base_trainer.BaseTrainer.construct_ground_truth = trainer_glue.construct_ground_truth

@@ -1,5 +1,7 @@
 """python -m neddf_b200.launch <reference script.py> [args...]: run a reference entry point
-(neddf/scripts/run.py, run_eval.py) with NeRFRender / NeDDF rebound to the B200 classes."""
+(neddf/scripts/run.py, run_eval.py) with NeRFRender / NeDDF rebound to the B200 classes.
+NEDDF_B200_PATCH_TRAINER=1 also swaps in the vectorised ground-truth gather (trainer_glue.py)."""
+import os
 import runpy
 import sys
 
@@ -9,7 +11,7 @@ def main() -> None:
         raise SystemExit(__doc__)
     from .install import install
 
-    install()
+    install(patch_trainer=os.environ.get("NEDDF_B200_PATCH_TRAINER", "0") not in ("", "0"))
     script = sys.argv[1]
     sys.argv = sys.argv[1:]
     runpy.run_path(script, run_name="__main__")

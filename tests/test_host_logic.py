@@ -80,3 +80,64 @@ def test_install_rebinds_reference_targets(repo_root):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join(["/root/reference", os.path.join(repo_root, "tests/golden/_refstub"), repo_root]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def _loop_targets(item, us_int, vs_int, loss_types):
+    """Restatement of the per-pixel loop of base_trainer.py:222-243 (test oracle)."""
+    out = {}
+    if "ColorLoss" in loss_types:
+        rgb = item["rgb_images"]
+        out["color"] = torch.from_numpy(((1.0 / 256) * np.stack([rgb[v, u, :] for u, v in zip(us_int, vs_int)])).astype(np.float32))
+    if "MaskBCELoss" in loss_types or "MaskMSELoss" in loss_types:
+        mask = item["mask_images"]
+        out["mask"] = torch.from_numpy(((1.0 / 256) * np.stack([mask[v, u] for u, v in zip(us_int, vs_int)])).astype(np.float32))
+    if "FieldsConstraintLoss" in loss_types:
+        out["fields_penalty"] = torch.zeros(us_int.shape, dtype=torch.float32)
+    return out
+
+
+def test_vectorised_ground_truth_gather_is_bit_exact():
+    from neddf_b200.trainer_glue import gather_targets
+    rng = np.random.default_rng(0)
+    item = {"rgb_images": rng.integers(0, 256, (37, 53, 3), dtype=np.uint8),
+            "mask_images": rng.integers(0, 256, (37, 53), dtype=np.uint8)}
+    g = torch.Generator().manual_seed(1)
+    us = (torch.rand(300, generator=g) * 52).to(torch.int16)  # nerf_trainer.py:92-97
+    vs = (torch.rand(300, generator=g) * 36).to(torch.int16)
+    kinds = ["ColorLoss", "MaskBCELoss", "FieldsConstraintLoss"]
+    got, ref = gather_targets(item, us, vs, kinds, "cpu"), _loop_targets(item, us, vs, kinds)
+    assert set(got) == set(ref) == {"color", "mask", "fields_penalty"}
+    for k in ref:
+        assert got[k].dtype == torch.float32 and got[k].shape == ref[k].shape and torch.equal(got[k], ref[k]), k
+    assert set(gather_targets(item, us, vs, ["MaskMSELoss"], "cpu")) == {"mask"}
+    assert gather_targets(item, us[:0], vs[:0], ["ColorLoss"], "cpu")["color"].shape == (0, 3)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/neddf"), reason="reference tree not present")
+def test_trainer_patch_matches_reference_method(repo_root):
+    """install(patch_trainer=True) swaps BaseTrainer.construct_ground_truth for the vectorised gather;
+    the reference's own method gives the same tensors (subprocess; skimage/hydra stubbed)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, types, numpy as np, torch\n"
+        "sk = types.ModuleType('skimage'); m = types.ModuleType('skimage.metrics')\n"
+        "m.peak_signal_noise_ratio = m.structural_similarity = None; sk.metrics = m\n"
+        "sys.modules['skimage'] = sk; sys.modules['skimage.metrics'] = m\n"
+        "from neddf.trainer.base_trainer import BaseTrainer\n"
+        "ref_fn = BaseTrainer.construct_ground_truth\n"
+        "import neddf_b200.install as I; I.install(patch_trainer=True)\n"
+        "assert BaseTrainer.construct_ground_truth is not ref_fn\n"
+        "rng = np.random.default_rng(3)\n"
+        "class T: pass\n"
+        "t = T(); t.device = torch.device('cpu')\n"
+        "t.dataset = [dict(rgb_images=rng.integers(0, 256, (20, 30, 3), dtype=np.uint8), mask_images=rng.integers(0, 256, (20, 30), dtype=np.uint8))]\n"
+        "us = (torch.rand(64) * 29).to(torch.int16); vs = (torch.rand(64) * 19).to(torch.int16)\n"
+        "kinds = ['ColorLoss', 'MaskBCELoss', 'FieldsConstraintLoss']\n"
+        "a = ref_fn(t, 0, us, vs, kinds); b = BaseTrainer.construct_ground_truth(t, 0, us, vs, kinds)\n"
+        "assert set(a) == set(b) and all(torch.equal(a[k], b[k]) and a[k].dtype == b[k].dtype for k in a)\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(["/root/reference", os.path.join(repo_root, "tests/golden/_refstub"), repo_root]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
