@@ -146,10 +146,11 @@ def cpu_port_rate(n_rays: int, threads: int):
     return n_rays * NOMINAL_PER_RAY / dt, dt
 
 
-def best_cpu_threads() -> int:
+def best_cpu_threads():
     """Thread count for the CPU arm: the batched small GEMMs of the reference path do not scale to
     every core of a big host (128 threads measured 10x slower than 8 on the same work), so a tiny
-    probe picks the fastest of a few counts - the baseline gets its best configuration."""
+    probe picks the fastest of a few counts - the baseline gets its best configuration.
+    Returns (threads, ray-samples/s of the probe)."""
     n = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
     best, best_rate = cands[0], 0.0
@@ -157,17 +158,25 @@ def best_cpu_threads() -> int:
         r, _ = cpu_port_rate(48, c)
         if r > best_rate:
             best, best_rate = c, r
-    return best
+    return best, best_rate
+
+
+def bounded_cpu_rays(max_rays: int, rate: float, seconds: float) -> int:
+    """Rays in one CPU sample: at most `max_rays`, sized from the probe rate to about `seconds`."""
+    if rate <= 0:
+        return max_rays
+    return int(max(48, min(max_rays, rate * seconds / NOMINAL_PER_RAY)))
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on
-    the GPU box) timed on host cores, same workload/metric, bounded sample per step."""
+    the GPU box) timed on host cores, same workload/metric, bounded sample per step (about 10 s of
+    CPU work each, so that W + K steps end within a few minutes on any host)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = best_cpu_threads()
-    n_rays = args.cpu_rays
+    threads, probe_rate = best_cpu_threads()
+    n_rays = bounded_cpu_rays(args.cpu_rays, probe_rate, 10.0)
     rates = []
     for i in range(args.warmup + args.steps):
         r, dt = cpu_port_rate(n_rays, threads)
@@ -354,10 +363,11 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        threads = best_cpu_threads()
-        v, dt = cpu_port_rate(args.cpu_rays, threads)
+        threads, probe_rate = best_cpu_threads()
+        cpu_rays = bounded_cpu_rays(args.cpu_rays, probe_rate, 20.0)
+        v, dt = cpu_port_rate(cpu_rays, threads)
         cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_rays} random rays of the same 800x800 frame ({args.cpu_rays * EVALS_PER_RAY} MLP evaluations, {dt:.1f} s)"}
+               "sample": f"{cpu_rays} random rays of the same 800x800 frame ({cpu_rays * EVALS_PER_RAY} MLP evaluations, {dt:.1f} s)"}
 
     if rank == 0:
         engine = render.network_fine.resolved_engine(dev)
