@@ -362,7 +362,7 @@ def main():
     d2h = n_frames * n_pix * 4 * 4 if rank == 0 else 0
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:  # reported at N=1 only
         threads, probe_rate = best_cpu_threads()
         cpu_rays = bounded_cpu_rays(args.cpu_rays, probe_rate, 20.0)
         v, dt = cpu_port_rate(cpu_rays, threads)
