@@ -59,3 +59,26 @@ def test_layer_shapes_and_validation(built):
     cfg = bad._config_struct()
     assert lib.neddf_field_layer_shapes(C.byref(cfg), None, 0) == -3  # NEDDF_E_UNSUPPORTED
     assert b"256" in lib.neddf_last_error()
+
+
+def test_entry_points_fail_loudly_without_a_gpu(built):
+    """No CPU fallback: with no CUDA device (this container) creating a field returns an error code
+    and a message, NULL arguments are rejected before any CUDA call, nothing crashes or leaks a handle."""
+    import ctypes as C
+
+    import torch
+
+    import neddf_b200
+    from neddf_b200 import _lib as L
+    lib = L.lib()
+    assert lib.neddf_field_create(None, None) < 0 and lib.neddf_last_error()
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    cfg = neddf_b200.NeDDF()._config_struct()
+    handle = C.c_void_p()
+    rc = lib.neddf_field_create(C.byref(cfg), C.byref(handle))
+    assert rc < 0 and not handle.value
+    assert b"CUDA" in lib.neddf_last_error() or b"cuda" in lib.neddf_last_error()
+    assert lib.neddf_field_destroy(None) in (0, -1, -2)  # tolerated, never a crash
+    with pytest.raises(Exception):  # the Python surface refuses CPU tensors instead of computing on the host
+        neddf_b200.NeDDF()(neddf_b200.Sampling(torch.zeros(1, 2, 3), torch.zeros(1, 2, 3), torch.zeros(1, 2, 3)))
