@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NEDDF_ABI_VERSION 1
+#define NEDDF_ABI_VERSION 2
 
 #define NEDDF_OK 0
 #define NEDDF_E_INVALID (-1)     /* bad argument / unsupported configuration */
@@ -84,6 +84,9 @@ typedef struct neddf_field_state {
   float aux_grad_scale;
   float distance_range_max;
   float lowpass_alpha;
+  /* penalty weights as the reference reads them: from the module's dict on EVERY forward
+   * (neddf.py:296-299), same order as neddf_field_config_t.penalty_weight */
+  float penalty_weight[NEDDF_N_PENALTY];
 } neddf_field_state_t;
 
 typedef struct neddf_field neddf_field_t; /* opaque: config + packed device weights */
@@ -174,7 +177,7 @@ int32_t neddf_field_forward_train(const neddf_field_t* f, const neddf_field_stat
                                   const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
                                   int64_t n_rays, int32_t n_edges, int32_t sampling_type, float ray_radius,
                                   float* d_density, float* d_color, float* d_penalty, float* d_save_pre,
-                                  void* stream);
+                                  int32_t engine, void* stream);
 
 /* Backward of NeDDF.forward (the reference's hand-written backward passes, nn_module/with_grad
  * linear.py:49-84, tanh_exp.py:57-88, softplus.py:55-89, sigmoid.py:49-83, and autograd through
@@ -199,7 +202,7 @@ int32_t neddf_field_backward(const neddf_field_t* f, const neddf_field_state_t* 
 int32_t neddf_field_forward_train_samples(const neddf_field_t* f, const neddf_field_state_t* st,
                                           const float* d_pos, const float* d_dir, const float* d_var, int64_t n,
                                           float* d_distance, float* d_density, float* d_color, float* d_penalty,
-                                          float* d_aux_grad, float* d_save_pre, void* stream);
+                                          float* d_aux_grad, float* d_save_pre, int32_t engine, void* stream);
 int32_t neddf_field_backward_samples(const neddf_field_t* f, const neddf_field_state_t* st, const float* d_pos,
                                      const float* d_dir, const float* d_var, int64_t n, const float* d_save_pre,
                                      const float* g_density, const float* g_color, const float* g_penalty,
@@ -235,7 +238,9 @@ int32_t neddf_composite_backward(const float* d_dists, const float* d_density, c
  *      zeroed in place exactly as the reference does to its argument, :52-55), u[n_rays,n_new]
  * out: dists_fine[n_rays, n_edges+n_new] sorted; optional ids[n_rays,n_new] (int64,
  *      searchsorted right=True) and cdf[n_rays,n_edges].  The batch-wide NaN fallback
- *      (base_neural_render.py:105-114) is applied on device; d_status bit1 records it. */
+ *      (base_neural_render.py:105-114) is applied on device, per launch like the reference:
+ *      d_status (optional) points to TWO int32 - [0] persistent flags (bit1 = "pdf sampling failed"
+ *      happened since the host last cleared it), [1] scratch holding this launch's decision. */
 int32_t neddf_sample_pdf(const float* d_dists, float* d_weights, const float* d_u,
                          int64_t n_rays, int32_t n_edges, int32_t n_new, float* d_dists_fine,
                          int64_t* d_ids, float* d_cdf, int32_t* d_status, void* stream);
@@ -265,6 +270,20 @@ int32_t neddf_tc_selftest_ts(const float* d_a, const float* d_b, int32_t k, floa
  * d_cycles[0] = SM cycles to issue, d_cycles[1] = cycles until the last MMA completed. */
 int32_t neddf_tc_mma_bench(int32_t a_mn, int32_t b_mn, int32_t swizzle, int32_t n, int32_t reps,
                            int64_t* d_cycles, void* stream);
+
+/* Self-test of the CTA-pair MMA (tcgen05.mma.cta_group::2, cluster of two CTAs on one TPC):
+ * C[256,n] = A[256,k] B[n,k]^T with A written to tensor memory by each CTA (rows 128r..128r+127) and
+ * B MN-major in shared memory (CTA r holds rows (n/2)r..(n/2)(r+1)-1); averaged over `reps`
+ * accumulations; d_cycles[0] (optional) = SM cycles for reps*k/16*3 MMAs.  Pins the operand split,
+ * the multicast commit and the accumulator layout the pair kernel (field_tc2.cu) relies on. */
+int32_t neddf_tc_pair_selftest(const float* d_a, const float* d_b, int32_t n, int32_t k, float* d_c,
+                               int64_t* d_cycles, int32_t reps, void* stream);
+
+/* Distributed-shared-memory store rate (profiling aid): every CTA of n_clusters CTA pairs writes
+ * `bytes` x reps with 16-byte st.shared::cluster (mode 0 = own shared memory, 1 = both CTAs into the
+ * peer, 2 = rank 0 into rank 1 only, 3 = like 1 with 512-byte blocks permuted).  d_cycles[cta]. */
+int32_t neddf_dsmem_bench(int32_t mode, int32_t reps, int32_t bytes, int32_t n_clusters, int64_t* d_cycles,
+                          void* stream);
 
 #ifdef __cplusplus
 }

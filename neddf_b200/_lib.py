@@ -36,7 +36,8 @@ class FieldConfig(C.Structure):
 
 
 class FieldState(C.Structure):
-    _fields_ = [("aux_grad_scale", C.c_float), ("distance_range_max", C.c_float), ("lowpass_alpha", C.c_float)]
+    _fields_ = [("aux_grad_scale", C.c_float), ("distance_range_max", C.c_float), ("lowpass_alpha", C.c_float),
+                ("penalty_weight", C.c_float * N_PENALTY)]
 
 
 _P = C.c_void_p
@@ -61,10 +62,12 @@ _SIGNATURES = {
     "neddf_field_forward": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _P]),
     "neddf_field_forward_rays": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _I32, _I32, _F,
                                         _P, _P, _P, _P, _P, _I32, _I32, _P]),
-    "neddf_field_forward_train": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
+    "neddf_field_forward_train": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P,
+                                         _I32, _P]),
     "neddf_field_backward": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P]),
-    "neddf_field_forward_train_samples": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "neddf_field_forward_train_samples": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P,
+                                                 _I32, _P]),
     "neddf_field_backward_samples": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P,
                                             _P, _P, _P, _P]),
     "neddf_composite": (_I32, [_P, _P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P, _P]),
@@ -74,6 +77,8 @@ _SIGNATURES = {
     "neddf_tc_mma_bench": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _P]),
     "neddf_tc_selftest_ts": (_I32, [_P, _P, _I32, _P, _P, _I32, _P]),
     "neddf_tc_selftest": (_I32, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "neddf_tc_pair_selftest": (_I32, [_P, _P, _I32, _I32, _P, _P, _I32, _P]),
+    "neddf_dsmem_bench": (_I32, [_I32, _I32, _I32, _I32, _P, _P]),
 }
 
 _lib = None
@@ -96,7 +101,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.neddf_abi_version() != 1:
+        if handle.neddf_abi_version() != 2:
             raise RuntimeError("neddf_b200: ABI version mismatch between Python host and libneddf_b200.so")
         _lib = handle
     return _lib

@@ -304,6 +304,7 @@ static int32_t fill_state(const neddf_field* f, const neddf_field_state_t* st, F
   if (!st) return fail(NEDDF_E_INVALID, "field state is NULL");
   p.aux_grad_scale = st->aux_grad_scale;
   p.distance_range_max = st->distance_range_max;
+  for (int i = 0; i < NEDDF_N_PENALTY; ++i) p.penalty_weight[i] = st->penalty_weight[i];
   // PositionalEncodingGradLayer.get_lowpass_scale (positional_encoding.py:137-157): the
   // reference evaluates the window in Python doubles and stores it as fp32
   const int E = f->cfg.embed_pos_rank;
@@ -396,7 +397,7 @@ extern "C" int32_t neddf_field_forward_train(const neddf_field_t* f, const neddf
                                              const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
                                              int64_t n_rays, int32_t n_edges, int32_t sampling_type, float ray_radius,
                                              float* d_density, float* d_color, float* d_penalty, float* d_save_pre,
-                                             void* stream) {
+                                             int32_t engine, void* stream) {
   FieldParams p;
   int32_t rc = fill_rays(f, st, p, d_ray_dir, d_ray_orig, d_dists, n_rays, n_edges, sampling_type, ray_radius,
                          "neddf_field_forward_train");
@@ -404,9 +405,8 @@ extern "C" int32_t neddf_field_forward_train(const neddf_field_t* f, const neddf
   if (!d_save_pre) return fail(NEDDF_E_INVALID, "neddf_field_forward_train: d_save_pre is NULL");
   p.density = d_density; p.color = d_color; p.penalty = d_penalty;
   p.save_pre = d_save_pre;
-  // the tensor-core engine produces the same saved pre-activations (to ~1e-5); the backward itself
-  // is the fp32 kernel either way
-  return dispatch(f, p, NEDDF_OUT_FULL, NEDDF_ENGINE_AUTO, (cudaStream_t)stream);
+  // the tensor-core engine produces the same saved pre-activations (to ~1e-5) as the fp32 one
+  return dispatch(f, p, NEDDF_OUT_FULL, engine, (cudaStream_t)stream);
 }
 
 extern "C" int32_t neddf_field_backward(const neddf_field_t* f, const neddf_field_state_t* st, const float* d_ray_dir,
@@ -447,14 +447,14 @@ extern "C" int32_t neddf_field_forward_train_samples(const neddf_field_t* f, con
                                                      const float* d_pos, const float* d_dir, const float* d_var,
                                                      int64_t n, float* d_distance, float* d_density, float* d_color,
                                                      float* d_penalty, float* d_aux_grad, float* d_save_pre,
-                                                     void* stream) {
+                                                     int32_t engine, void* stream) {
   FieldParams p;
   int32_t rc = fill_samples(f, st, p, d_pos, d_dir, d_var, n, "neddf_field_forward_train_samples");
   if (rc != NEDDF_OK) return rc;
   if (!d_save_pre) return fail(NEDDF_E_INVALID, "neddf_field_forward_train_samples: d_save_pre is NULL");
   p.distance = d_distance; p.density = d_density; p.color = d_color; p.penalty = d_penalty; p.aux_grad = d_aux_grad;
   p.save_pre = d_save_pre;
-  return dispatch(f, p, NEDDF_OUT_FULL, NEDDF_ENGINE_AUTO, (cudaStream_t)stream);
+  return dispatch(f, p, NEDDF_OUT_FULL, engine, (cudaStream_t)stream);
 }
 
 extern "C" int32_t neddf_field_backward_samples(const neddf_field_t* f, const neddf_field_state_t* st,

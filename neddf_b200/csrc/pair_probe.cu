@@ -1,0 +1,157 @@
+// Hardware probes for the CTA-pair (cta_group::2) field kernel: they pin the conventions the kernel
+// relies on and measure the two rates its design rests on.
+//
+//   neddf_tc_pair_selftest : C[256, n] = A[256, k] * B[n, k]^T with one tcgen05.mma.cta_group::2 per
+//       K-step and product (A = "weights", fp16 hi/lo, written to each CTA's tensor memory with
+//       tcgen05.st: CTA r owns rows 128r..128r+127; B = "activations", fp16 hi/lo, MN-major in shared
+//       memory: CTA r owns rows (n/2)r..(n/2)(r+1)-1).  Checks the operand split between the two CTAs,
+//       the multicast commit and the accumulator layout; also times `reps` repetitions.
+//   neddf_dsmem_bench      : 16-byte st.shared::cluster stores into the peer CTA's shared memory
+//       (the activation exchange of the pair kernel), bytes per cycle.
+#include <cooperative_groups.h>
+
+#include "tc_ptx.cuh"
+
+namespace neddf {
+namespace tc {
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    tc_pair_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int n, int k,
+                            float* __restrict__ C, long long* __restrict__ cyc, int reps) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* h_hi = smem;
+  unsigned char* h_lo = smem + kHBytes;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nh = n / 2;  // B rows held by this CTA
+  for (int idx = tid; idx < nh * k; idx += 128) {
+    int kk = idx % k, r = idx / k;
+    float b = B[(size_t)(nh * rank + r) * k + kk];
+    __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
+    *reinterpret_cast<__half*>(h_hi + act_off(r, kk, kHK)) = hi;
+    *reinterpret_cast<__half*>(h_lo + act_off(r, kk, kHK)) = lo;
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc2(&tmem_base, 512);
+  fence_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  // A: lane = row m of this CTA's half; per K-step 8 columns hi at 256 + ks*16, 8 columns lo after
+  const int m = 32 * warp + lane;
+  for (int ks = 0; ks < k / 16; ++ks) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a0 = A[(size_t)(128 * rank + m) * k + ks * 16 + 2 * j], a1 = A[(size_t)(128 * rank + m) * k + ks * 16 + 2 * j + 1];
+      float amax = 0.f;
+      split2(a0, a1, hi[j], lo[j], amax);
+    }
+    const uint32_t ta = tmem + ((uint32_t)(32 * warp) << 16) + 256 + ks * 16;
+    tmem_st8(ta, hi);
+    tmem_st8(ta + 8, lo);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == 0 && rank == 0) {
+    const uint32_t s_hhi = smem_u32(h_hi), s_hlo = smem_u32(h_lo);
+    const uint32_t idesc = make_idesc(256, n, 0, 1);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int ks = 0; ks < k / 16; ++ks) {
+        const uint64_t db_hi = make_desc(s_hhi + ks * 256, 128, kHK * 16), db_lo = make_desc(s_hlo + ks * 256, 128, kHK * 16);
+        const uint32_t ta = tmem + 256 + ks * 16;
+        mma2_f16_ts_elect(tmem, ta, db_hi, idesc, (r | ks) > 0);
+        mma2_f16_ts_elect(tmem, ta + 8, db_hi, idesc, 1);
+        mma2_f16_ts_elect(tmem, ta, db_lo, idesc, 1);
+      }
+    }
+    mma2_commit_elect(smem_u32(&bar), 3);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (lane == 0 && cyc) cyc[0] = t1 - t0;
+  } else {
+    mbar_wait(&bar, 0);
+  }
+  __syncthreads();
+  tc_fence_after();
+  for (int cb = 0; cb < n / 16; ++cb) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + cb * 16, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) C[(size_t)(128 * rank + m) * n + cb * 16 + i] = v[i] / (float)reps;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem, 512);
+}
+
+// mode 0: local st.shared.v4; 1: both CTAs store into the peer; 2: only rank 0 stores into rank 1;
+// 3: both store into the peer with a 512-byte-per-warp contiguous pattern (as the pair kernel's
+//    epilogue does) but the warp's rows 2 KB apart (different row groups)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+    dsmem_bench_kernel(int mode, int reps, int bytes, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x;
+  const uint32_t local = smem_u32(smem);
+  const uint32_t peer = mapa_u32(local, rank ^ 1u);
+  for (int i = tid; i < bytes / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  cluster_sync_all();
+  const bool active = (mode == 0) || (mode == 1) || (mode == 3) || (mode == 2 && rank == 0);
+  const uint32_t base = (mode == 0) ? local : peer;
+  long long t0 = clock64();
+  if (active) {
+    for (int r = 0; r < reps; ++r) {
+      for (int off = tid * 16; off < bytes; off += 512 * 16) {
+        uint32_t o = off;
+        if (mode == 3) {  // permute 512-byte blocks
+          uint32_t blk = off >> 9, in = off & 511;
+          o = (((blk * 5) % (bytes >> 9)) << 9) | in;
+        }
+        st_cluster_v4(base + o, make_uint4(r, tid, off, 1));
+      }
+    }
+  }
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  cluster_sync_all();
+  long long t1 = clock64();
+  if (tid == 0) out[blockIdx.x] = t1 - t0;
+  // keep the stores observable
+  if (tid == 0 && reinterpret_cast<volatile uint32_t*>(smem)[3] == 0xdeadbeefu) out[blockIdx.x] = -1;
+}
+
+}  // namespace tc
+}  // namespace neddf
+
+using namespace neddf;
+
+extern "C" int32_t neddf_tc_pair_selftest(const float* d_a, const float* d_b, int32_t n, int32_t k, float* d_c,
+                                          int64_t* d_cycles, int32_t reps, void* stream) {
+  if (k < 16 || k > 256 || (k % 16) != 0 || reps < 1 || n < 32 || n > 256 || (n % 32) != 0)
+    return fail(NEDDF_E_INVALID, "neddf_tc_pair_selftest: need k in [16,256] (multiple of 16), n in [32,256] (multiple of 32)");
+  if (!d_a || !d_b || !d_c) return fail(NEDDF_E_INVALID, "neddf_tc_pair_selftest: NULL pointer");
+  size_t smem = 2 * tc::kHBytes;
+  NEDDF_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::tc_pair_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(d_a, d_b, n, k, d_c, reinterpret_cast<long long*>(d_cycles), reps);
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}
+
+extern "C" int32_t neddf_dsmem_bench(int32_t mode, int32_t reps, int32_t bytes, int32_t n_clusters, int64_t* d_cycles,
+                                     void* stream) {
+  if (mode < 0 || mode > 3 || reps < 1 || bytes < 8192 || bytes > 196608 || (bytes % 8192) != 0 || n_clusters < 1 || !d_cycles)
+    return fail(NEDDF_E_INVALID, "neddf_dsmem_bench: bad arguments");
+  NEDDF_CUDA_CHECK(cudaFuncSetAttribute(tc::dsmem_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  tc::dsmem_bench_kernel<<<2 * n_clusters, 512, bytes, (cudaStream_t)stream>>>(mode, reps, bytes, reinterpret_cast<long long*>(d_cycles));
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}

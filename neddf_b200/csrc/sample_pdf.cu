@@ -127,14 +127,17 @@ sample_pdf_kernel(const float* __restrict__ dists, float* __restrict__ weights, 
     for (int j = lane; j < n_out; j += 32) dists_fine[ray * n_out + j] = s_merge[j];
     __syncwarp();
   }
-  if (status && __any_sync(0xffffffffu, saw_nan) && lane == 0) atomicOr(status, 2);
+  if (status && __any_sync(0xffffffffu, saw_nan) && lane == 0) atomicOr(status + 1, 2);  // this launch's flag
 }
 
-// Batch-wide fallback of the reference (:105-114): if any merged sample was NaN, every ray gets
-// linspace(dists[0,0], dists[0,-1], n_out).  Runs on device so the host never synchronises.
-__global__ void pdf_nan_fallback_kernel(const int* __restrict__ status, const float* __restrict__ dists,
+// Batch-wide fallback of the reference (:105-114): if any merged sample of THIS launch was NaN, every
+// ray of the batch gets linspace(dists[0,0], dists[0,-1], n_out).  Runs on device so the host never
+// synchronises.  status[1] is the per-launch flag (zeroed before sample_pdf_kernel); it is folded into
+// the persistent word status[0] that the host reads and clears (the reference prints each time).
+__global__ void pdf_nan_fallback_kernel(int* __restrict__ status, const float* __restrict__ dists,
                                         int n_edges, int64_t total, int n_out, float* __restrict__ dists_fine) {
-  if ((*status & 2) == 0) return;
+  if ((status[1] & 2) == 0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 2);
   float a = dists[0], b = dists[n_edges - 1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     dists_fine[i] = linspace_at(a, b, n_out, (int)(i % n_out));
@@ -174,6 +177,7 @@ extern "C" int32_t neddf_sample_pdf(const float* d_dists, float* d_weights, cons
   int64_t blocks = (n_rays + kPdfWarps - 1) / kPdfWarps;
   int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (d_status) NEDDF_CUDA_CHECK(cudaMemsetAsync(d_status + 1, 0, sizeof(int32_t), s));
   sample_pdf_kernel<<<(unsigned)blocks, kPdfWarps * 32, smem, s>>>(d_dists, d_weights, d_u, n_rays, n_edges, n_new,
                                                                    p2, d_dists_fine, d_ids, d_cdf, d_status);
   NEDDF_LAUNCH_CHECK();

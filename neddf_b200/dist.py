@@ -67,6 +67,8 @@ def render_image_sharded(render, width: int, height: int, camera, target_types: 
     if uniforms is not None:
         u = (uniforms[0][first:first + count], uniforms[1][first:first + count])
     flat = render.render_pixels(width, height, camera, target_types, downsampling, first, count, u)
+    if getattr(render, "check_nan", False):
+        render.check_status()  # NaN weights raise, a failed resampling is reported - like render_image
     widths = [flat[k].shape[1] for k in target_types]
     packed = torch.cat([flat[k] for k in target_types], 1) if len(target_types) > 1 else flat[target_types[0]]
     full = gather_tiles(packed, n_pix, group)

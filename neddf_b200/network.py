@@ -40,10 +40,10 @@ class LinearGradLayer(nn.Module):
 
 
 class _FieldTrainFn(torch.autograd.Function):
-    """Differentiable NeDDF.forward on rays + edge distances (training path, fp32 engine).
+    """Differentiable NeDDF.forward on rays + edge distances (training path).
 
-    forward : neddf_field_forward_train - the fused fp32 megakernel, keeping every layer's
-              pre-activations.
+    forward : neddf_field_forward_train - the fused megakernel of the module's engine (``net.engine``:
+              tensor-core by default, "fp32" on request), keeping every layer's pre-activations.
     backward: neddf_field_backward does all sample-local work (activation second derivatives, heads,
               density, penalties, data-gradient GEMMs) and writes per-layer inputs X_l and
               pre-activation gradients G_l; the weight gradients gW_l = X_l^T G_l are plain GEMMs over
@@ -73,14 +73,16 @@ class _FieldTrainFn(torch.autograd.Function):
             if from_rays:
                 L.check(L.lib().neddf_field_forward_train(
                     h, C.byref(st), L.ptr(a), L.ptr(b), L.ptr(c), B, S, L.SAMPLING_IDS[sampling_type],
-                    float(ray_radius), L.ptr(density), L.ptr(color), L.ptr(penalty), L.ptr(save), L.stream_ptr(device)),
-                    "field_forward_train")
+                    float(ray_radius), L.ptr(density), L.ptr(color), L.ptr(penalty), L.ptr(save),
+                    L.ENGINE_IDS[net.engine], L.stream_ptr(device)), "field_forward_train")
             else:
                 L.check(L.lib().neddf_field_forward_train_samples(
                     h, C.byref(st), L.ptr(a), L.ptr(b), L.ptr(c), n, L.ptr(distance), L.ptr(density), L.ptr(color),
-                    L.ptr(penalty), L.ptr(aux), L.ptr(save), L.stream_ptr(device)), "field_forward_train_samples")
+                    L.ptr(penalty), L.ptr(aux), L.ptr(save), L.ENGINE_IDS[net.engine], L.stream_ptr(device)),
+                    "field_forward_train_samples")
         ctx.net = net
-        ctx.meta = (sampling_type, float(ray_radius), (st.aux_grad_scale, st.distance_range_max, st.lowpass_alpha), (B, S))
+        ctx.meta = (sampling_type, float(ray_radius),
+                    (st.aux_grad_scale, st.distance_range_max, st.lowpass_alpha, tuple(st.penalty_weight)), (B, S))
         ctx.save_for_backward(a, b, c, save)
         if from_rays:
             return density, color, penalty
@@ -115,7 +117,7 @@ class _FieldTrainFn(torch.autograd.Function):
         xes = torch.empty(n, 4, n_e0, device=device, dtype=torch.float32)
         xcol = torch.empty(n, 4, off_h, device=device, dtype=torch.float32)
         h = net._field(device)
-        st = L.FieldState(*stv)
+        st = L.FieldState(stv[0], stv[1], stv[2], (C.c_float * L.N_PENALTY)(*stv[3]))
         with torch.cuda.device(device):
             if from_rays:
                 L.check(L.lib().neddf_field_backward(
@@ -274,7 +276,10 @@ class NeDDF(BaseNeuralField):
         return c
 
     def _state_struct(self) -> L.FieldState:
-        return L.FieldState(float(self.aux_grad_scale), float(self.distance_range_max), float(self.lowpass_alpha))
+        """Per-call scalars: the warm-up schedule and the penalty weights, both read from the module on
+        every forward like the reference does (neddf.py:296-299: absent key -> unweighted)."""
+        pw = (C.c_float * L.N_PENALTY)(*[float(self.penalty_weight.get(k, 1.0)) for k in L.PENALTY_KEYS])
+        return L.FieldState(float(self.aux_grad_scale), float(self.distance_range_max), float(self.lowpass_alpha), pw)
 
     def _release(self) -> None:
         if self._handle is not None:
@@ -305,8 +310,7 @@ class NeDDF(BaseNeuralField):
                 L.check(lib.neddf_field_create(C.byref(cfg), C.byref(h)), "field_create")
             self._handle, self._handle_device = h, device
         layers = self._ordered_layers()
-        key = tuple((p.data_ptr(), p._version) for l in layers for p in (l.weight, l.bias)) + (
-            tuple(sorted(self.penalty_weight.items())),)
+        key = tuple((p.data_ptr(), p._version) for l in layers for p in (l.weight, l.bias))
         if key != self._packed_key:
             n = len(layers)
             ws = (C.c_void_p * n)(*[l.weight.data_ptr() for l in layers])
@@ -323,6 +327,30 @@ class NeDDF(BaseNeuralField):
         r = super()._apply(fn, *a, **k)
         self._packed_key = None  # .to()/.cuda() replaced the parameter storage
         return r
+
+    def invalidate(self) -> None:
+        """Force a re-pack of the kernel-layout weights on the next call.  Needed only after edits that
+        bypass the parameters' version counters (``p.data.copy_(...)``, EMA swaps through ``.data``);
+        optimiser steps, ``load_state_dict`` and ``.to()`` are detected automatically."""
+        self._packed_key = None
+
+    # the kernel handle is a process-local pointer: copies and pickles get a fresh one lazily
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_handle"] = None
+        d["_handle_device"] = None
+        d["_packed_key"] = None
+        d["_profile_events"] = None
+        return d
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     # ------------------------------------------------------------------------- forward --
     def forward(self, sampling: Sampling) -> Dict[str, Tensor]:

@@ -190,7 +190,8 @@ class BaseNeuralRender(nn.Module):
     def _status(self, device) -> Tensor:
         st = getattr(self, "_status_buf", None)
         if st is None or st.device != device:
-            st = torch.zeros(1, device=device, dtype=torch.int32)
+            # [0] persistent flags read by check_status, [1] per-launch scratch of neddf_sample_pdf
+            st = torch.zeros(2, device=device, dtype=torch.int32)
             self._status_buf = st
         return st
 
@@ -205,7 +206,7 @@ class BaseNeuralRender(nn.Module):
         st = getattr(self, "_status_buf", None)
         if st is None:
             return
-        v = int(st.item())
+        v = int(st[0].item())
         st.zero_()
         if v & 1:
             raise AssertionError("NaN in volume-rendering weights (base_neural_render.py:155)")
@@ -409,7 +410,9 @@ class NeRFRender(BaseNeuralRender):
             pos = torch.stack([xs, ys, zs], 2).contiguous()
             sdir = torch.zeros_like(pos)
             sdir[:, :, 2] = 1.0
+            self.network_fine.train(False)  # nerf_render.py:309-311 toggles the mode around the query
             values = self.network_fine(Sampling(pos, sdir, torch.zeros_like(pos)))
+            self.network_fine.train(True)
             scales = {"distance": 256.0, "density": 12.8, "color": 256.0, "aux_grad": 256.0}
             fields: Dict[str, np.ndarray] = {}
             for key, scale in scales.items():

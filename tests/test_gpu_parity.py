@@ -149,6 +149,12 @@ def test_sample_pdf_sanitises_and_nan_fallback():
     out = render.sample_pdf(dn.to(G.DEV), w.clone().to(G.DEV), u.shape[1], uniform_rands=u.to(G.DEV))
     ref = torch.linspace(float(dn[0, 0]), float(dn[0, -1]), out.shape[1]).reshape(1, -1).expand(4, -1)
     assert nerr(out.cpu().numpy(), ref.numpy()) < 1e-6
+    # the fallback is per launch like the reference's: a clean batch right after a NaN batch is resampled
+    # normally although the host has not read/cleared the persistent flag yet
+    assert int(render._status_buf[0].item()) & 2
+    out = render.sample_pdf(dists.to(G.DEV), w.clone().to(G.DEV), u.shape[1], uniform_rands=u.to(G.DEV))
+    assert nerr(out.cpu().numpy(), orc.sample_pdf(dists, w.clone(), u).numpy()) < 5e-6
+    assert int(render._status_buf[0].item()) & 2  # still reported until check_status clears it
     render._status_buf.zero_()
 
 

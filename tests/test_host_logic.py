@@ -141,3 +141,37 @@ def test_trainer_patch_matches_reference_method(repo_root):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join(["/root/reference", os.path.join(repo_root, "tests/golden/_refstub"), repo_root]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_module_copies_and_pickles_without_the_kernel_handle():
+    """The reference module is deep-copyable / picklable (EMA copies, whole-module checkpoints); the
+    process-local kernel handle must not travel with it."""
+    import copy
+    import ctypes
+    import pickle
+    net = neddf_b200.NeDDF(col_layer_count=4)
+    net._handle = ctypes.c_void_p(1234)  # as after a first forward
+    net._handle_device = torch.device("cpu")
+    net._packed_key = ("stale",)
+    twin = copy.deepcopy(net)
+    assert twin._handle is None and twin._packed_key is None
+    assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr()
+               for a, b in zip(net.state_dict().values(), twin.state_dict().values()))
+    blob = pickle.dumps(net)
+    back = pickle.loads(blob)
+    assert back._handle is None and back.penalty_weight == net.penalty_weight
+    net._handle = None  # nothing real to destroy
+
+
+def test_state_struct_reads_penalty_weights_on_every_call():
+    """neddf.py:296-299 reads the dict on every forward: mutating it must reach the next launch."""
+    from neddf_b200 import _lib as L
+    net = neddf_b200.NeDDF(penalty_weight={"constraints_dDdt": 0.5})
+    st = net._state_struct()
+    w = dict(zip(L.PENALTY_KEYS, list(st.penalty_weight)))
+    assert w["constraints_dDdt"] == 0.5 and w["range_color"] == 1.0  # absent key -> unweighted
+    net.penalty_weight["range_color"] = 0.25
+    assert dict(zip(L.PENALTY_KEYS, list(net._state_struct().penalty_weight)))["range_color"] == 0.25
+    net._packed_key = ("x",)
+    net.invalidate()
+    assert net._packed_key is None
