@@ -17,6 +17,7 @@ copied from pinned memory, image copied back) inside the timed region.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -62,15 +63,32 @@ def synthetic_pose(seed: int):
     return R, T, np.array([focal, focal, 0.5 * W, 0.5 * H], dtype=np.float32)
 
 
+def seeded_params(seed: int = WEIGHT_SEED, bias_std: float = 0.05):
+    """Xavier-normal weights [in,out] like LinearGradLayer's init (nn_module/with_grad/linear.py:113-116)
+    from a fixed seed, biases perturbed so the bias path is exercised.  Built from the product's own
+    module (its parameter order is the reference's); tests/test_bench_contract.py pins that this is the
+    stream the oracle's init_params draws, so the CPU legs see identical weights."""
+    import math
+
+    import neddf_b200
+    net = neddf_b200.NeDDF(**{k: v for k, v in NET_CFG.items() if k != "_target_"})
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, v in net.state_dict().items():
+        if name.endswith(".weight"):
+            cin, cout = v.shape
+            out[name] = torch.randn(cin, cout, generator=g) * math.sqrt(2.0 / (cin + cout))
+        else:
+            out[name] = torch.randn(v.shape[0], generator=g) * bias_std
+    return out
+
+
 def seeded_state_dict():
-    """Xavier-normal weights [in,out] like LinearGradLayer's init, from a fixed seed (same
-    generator the oracle uses, so both arms see identical weights)."""
-    from oracle import neddf_oracle as orc
-    fc = orc.FieldConfig.from_dict(NET_CFG)
-    p = orc.init_params(fc, WEIGHT_SEED, bias_std=0.05)
+    """(state_dict of NeRFRender, per-network parameter dict) - no test infrastructure involved."""
+    p = seeded_params()
     sd = {"network_fine." + k: v for k, v in p.items()}
     sd.update({"network_coarse." + k: v for k, v in p.items()})
-    return sd, p, fc
+    return sd, p
 
 
 class ClockSampler:
@@ -123,12 +141,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_rate(n_rays: int, threads: int):
+def cpu_port_rate(n_rays: int, threads: int, keep=None):
     """The reference algorithm (oracle port, torch CPU fp32, same op structure as the reference)
-    on a bounded sample of the workload: `n_rays` rays of the same frame."""
+    on a bounded sample of the workload: `n_rays` rays of the same frame.  ``keep`` (a dict) receives
+    the sample's inputs and the port's outputs for the in-run parity check."""
     from oracle import neddf_oracle as orc
     torch.set_num_threads(threads)
-    sd, p, fc = seeded_state_dict()
+    _, p = seeded_state_dict()
+    fc = orc.FieldConfig.from_dict(NET_CFG)
     rc = orc.RenderConfig(**RENDER_CFG)
     st = orc.FieldState.at_iter(fc, -1)
     R, T, calib = synthetic_pose(0)
@@ -141,9 +161,39 @@ def cpu_port_rate(n_rays: int, threads: int):
     with torch.no_grad():
         orc.render_rays(p, p, fc, st, rc, uv[sel[:32]], cam, u_c[:32], u_f[:32])  # warm-up
         t0 = time.perf_counter()
-        orc.render_rays(p, p, fc, st, rc, uv[sel], cam, u_c, u_f)
+        taps = {} if keep is not None else None
+        out = orc.render_rays(p, p, fc, st, rc, uv[sel], cam, u_c, u_f, taps=taps)
         dt = time.perf_counter() - t0
+        if keep is not None:
+            cdf = orc.pdf_cdf(out["weight_coarse"])
+            _, ids = orc.invert_cdf(taps["dists_coarse"], cdf, u_f)
+            keep.update(uv=uv[sel], u_c=u_c, u_f=u_f, out=out, ids=ids)
     return n_rays * NOMINAL_PER_RAY / dt, dt
+
+
+def parity_block(render, cam, dev, keep):
+    """the CUDA path on the SAME rays and uniforms the CPU leg just
+    rendered.  max|new - ref| / max|ref| per output, and the end-to-end mismatch rate of the
+    searchsorted indices (bit-exact given the same cdf - tests/test_gpu_parity.py; here each side
+    inverts its own coarse weights)."""
+    uv, u_c, u_f, ref = keep["uv"].to(dev), keep["u_c"].to(dev), keep["u_f"].to(dev), keep["out"]
+    with torch.no_grad():
+        got = render.render_rays(uv, cam, uniforms=(u_c, u_f))
+        dists_c = torch.empty_like(u_c)
+        from neddf_b200 import _lib as L
+        L.check(L.lib().neddf_coarse_dists(L.ptr(u_c), u_c.shape[0], u_c.shape[1], render.dist_near, render.dist_far,
+                                           L.ptr(dists_c), L.stream_ptr(dev)), "coarse_dists")
+        _, ids = render.sample_pdf(dists_c, got["weight_coarse"].clone(), u_f.shape[1], uniform_rands=u_f, return_ids=True)
+    res = {}
+    for k in ("color", "depth", "transmittance", "fields_penalty", "color_coarse", "depth_coarse"):
+        a, b = got[k].detach().cpu().double(), ref[k].double()
+        res[k] = float((a.reshape(b.shape) - b).abs().max() / b.abs().max())
+    res["ids_mismatch_rate"] = float((ids.cpu() != keep["ids"]).double().mean())
+    mse = float(((got["color"].detach().cpu().double() - ref["color"].double()) ** 2).mean())
+    res["psnr_new_vs_ref_db"] = float("inf") if mse == 0 else 10.0 * math.log10(1.0 / mse)
+    res["rays"] = int(uv.shape[0])
+    res["reference"] = "oracle port (torch CPU fp32), same rays / uniforms / weights"
+    return res
 
 
 def best_cpu_threads():
@@ -206,18 +256,213 @@ def workload_config(n_gpus, engine):
             "l2": "per-frame uniforms are 497 MB (> 126 MB L2) and every step reads fresh ones; no explicit flush"}
 
 
+# --------------------------------------------------------------------------------------------------
+# workload "train": BASELINE.json configs[3] - the training inner loop (nerf_trainer.py:100-134) on 1 GPU
+# --------------------------------------------------------------------------------------------------
+TRAIN_RAYS = 1024           # config/trainer/nerf_trainer.yaml:3
+TRAIN_LR = 5e-4             # optimizer_lr
+# config/loss/neddf_loss.yaml: (weight, weight_coarse) of ColorLoss, MaskBCELoss, FieldsConstraintLoss
+LOSS_W = {"color": (1.0, 0.1), "mask": (0.05, 0.005), "fields_penalty": (0.01, 0.01)}
+
+
+def train_loss(out, target_color, target_mask):
+    """The reference's objective (loss/color_loss.py:41-55, mask_bce_loss.py:41-59,
+    fields_constraint_loss.py:40-54, summed as nerf_trainer.py:118-121) in plain torch ops."""
+    total = 0.0
+    for suffix, wi in (("", 0), ("_coarse", 1)):
+        total = total + LOSS_W["color"][wi] * torch.mean(torch.square(out["color" + suffix] - target_color))
+        m = torch.clamp(1.0 - out["transmittance" + suffix], 1e-6, 1.0 - 1e-6)
+        total = total + LOSS_W["mask"][wi] * -torch.mean(target_mask * torch.log(m) + (1.0 - target_mask) * torch.log(1.0 - m))
+        total = total + LOSS_W["fields_penalty"][wi] * torch.mean(out["fields_penalty" + suffix])
+    return total
+
+
+def train_batch(step: int, n_rays: int):
+    """Host-side batch like the trainer draws it: int16 pixel ids (nerf_trainer.py:100-106), synthetic
+    colour / mask targets (there is no dataset here)."""
+    g = torch.Generator().manual_seed(77 + step)
+    us = (torch.rand(n_rays, generator=g) * (W - 1)).to(torch.int16)
+    vs = (torch.rand(n_rays, generator=g) * (H - 1)).to(torch.int16)
+    uv = torch.stack([us, vs], 1)
+    color = torch.rand(n_rays, 3, generator=g)
+    mask = (torch.rand(n_rays, generator=g) > 0.5).float()
+    return uv, color, mask
+
+
+def cpu_port_train_rate(n_rays: int, threads: int):
+    """Forward + backward (autograd through the oracle port) + Adam on `n_rays` rays, host cores."""
+    from oracle import neddf_oracle as orc
+    torch.set_num_threads(threads)
+    _, p = seeded_state_dict()
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    fc = orc.FieldConfig.from_dict(NET_CFG)
+    rc = orc.RenderConfig(**RENDER_CFG)
+    R, T, calib = synthetic_pose(0)
+    cam = orc.CameraPose(torch.from_numpy(R), torch.from_numpy(T), *[float(c) for c in calib])
+    opt = torch.optim.Adam(list(p.values()), lr=TRAIN_LR)
+    dts = []
+    for it in range(2):
+        uv, color, mask = train_batch(it, n_rays)
+        g = torch.Generator().manual_seed(it)
+        u_c, u_f = torch.rand(n_rays, S_COARSE + 1, generator=g), torch.rand(n_rays, S_FINE + 1, generator=g)
+        st = orc.FieldState.at_iter(fc, it)
+        t0 = time.perf_counter()
+        out = orc.render_rays(p, p, fc, st, rc, uv.long(), cam, u_c, u_f)
+        loss = train_loss(out, color, mask)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        dts.append(time.perf_counter() - t0)
+    dt = dts[-1]
+    return n_rays * NOMINAL_PER_RAY / dt, dt
+
+
+def train_config(engine):
+    return {"workload": "drums-shaped synthetic training step: 1024 random pixels of an 800x800 view, 64 coarse + 128 "
+                        "fine samples/ray, forward + backward + Adam (nerf_trainer.py:100-134, neddf_loss.yaml), "
+                        "NeDDF 8x256 + 4x256 tanhExp, seeded random-init weights, set_iter(k)",
+            "rays_per_step": TRAIN_RAYS, "nominal_samples_per_ray": NOMINAL_PER_RAY,
+            "mlp_evaluations_per_ray": EVALS_PER_RAY, "engine": engine, "parallelism": "single GPU",
+            "l2": "1.3e9 B of per-step activations (> 126 MB L2) are written and re-read every step; no explicit flush"}
+
+
+def run_train(args):
+    metric = "ray-samples/s (training step, 1024 rays x 192)"
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = max(8, min(32, args.cpu_rays))
+        threads = min(32, os.cpu_count() or 1)
+        rates = []
+        for i in range(args.warmup + args.steps):
+            r, dt = cpu_port_train_rate(n, threads)
+            if i >= args.warmup:
+                rates.append((r, dt))
+        value = sum(r for r, _ in rates) / len(rates)
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": value, "unit": "ray-samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(d for _, d in rates) / len(rates),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": train_config("cpu"),
+            "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} rays per step: forward + autograd backward + Adam"},
+            "e2e": {"value": value, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}), flush=True)
+        return
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("bench.py --workload train is a single-GPU workload (BASELINE.json configs[3])")
+    import neddf_b200
+    from neddf_b200 import _lib as L
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the training path has no CPU implementation")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    sd, _ = seeded_state_dict()
+    render = neddf_b200.NeRFRender(network_config=NET_CFG, **RENDER_CFG)
+    render.load_state_dict(sd)
+    render.to(dev)
+    render.set_engine(args.engine)
+    render.check_nan = False
+    R, T, calib = synthetic_pose(0)
+    cam = neddf_b200.Camera.from_matrix(neddf_b200.PinholeCalib(calib), R, T).to(dev)
+    cam.update_transform()
+    opt = torch.optim.Adam(render.get_parameters_list(), lr=TRAIN_LR)
+    n_batches = 8
+    host = [tuple(x.pin_memory() for x in train_batch(i, TRAIN_RAYS)) for i in range(n_batches)]
+    resident = [tuple(x.to(dev) for x in b) for b in host]
+    it = [0]
+
+    def one_step(uv, color, mask):
+        render.set_iter(it[0])
+        it[0] += 1
+        out = render.render_rays(uv, cam)
+        loss = train_loss(out, color, mask)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_device(i):
+        return one_step(*resident[i % n_batches])
+
+    def step_e2e(i):
+        uv, color, mask = (x.to(dev, non_blocking=True) for x in host[i % n_batches])
+        return float(one_step(uv, color, mask).item())  # the loss the trainer logs (nerf_trainer.py:124)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for i in range(args.warmup):
+        step_device(i)
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = L.lib().neddf_launch_count()
+    ms_step = timed(step_device, args.steps)
+    launches = L.lib().neddf_launch_count() - launches0
+    clocks = sampler.stop()
+    render.check_status()
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    value = TRAIN_RAYS * NOMINAL_PER_RAY / (ms_step * 1e-3)
+    evals = TRAIN_RAYS * EVALS_PER_RAY
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = evals * 3 * F_FULL / (ms_step * 1e-3) / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = min(32, os.cpu_count() or 1)
+        v, dt = cpu_port_train_rate(16, threads)
+        cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
+               "sample": f"16 rays: forward + autograd backward + Adam ({dt:.1f} s)"}
+    engine = render.network_fine.resolved_engine(dev)
+    print(json.dumps({
+        "metric": metric, "value": value, "unit": "ray-samples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if engine == "fp32" else "f16x3-split operands, f32 accumulate (forward and data-gradient GEMMs); f32 elsewhere",
+        "data": "synthetic", "config": train_config(engine),
+        "mlp_evaluations_per_s": evals / (ms_step * 1e-3),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "kernel": "whole training step (field forward x2, field backward x2, weight gradients, Adam)",
+                     "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
+                     "flop_per_evaluation": 3 * F_FULL},
+        "cpu_baseline": cpu,
+        "e2e": {"value": TRAIN_RAYS * NOMINAL_PER_RAY / (ms_e2e * 1e-3), "unit": "ray-samples/s",
+                "h2d_bytes_per_step": TRAIN_RAYS * (2 * 2 + 3 * 4 + 4), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "peak_memory_gib": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc", "tc2"])
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render = BASELINE.json configs[1] (800x800 frame, the headline); train = configs[3] "
+                         "(1024-ray training step: forward + backward + Adam)")
     ap.add_argument("--cpu-rays", type=int, default=384, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rules: W >= 3
+    if args.workload == "train":
+        return run_train(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -239,7 +484,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
-    sd, _, _ = seeded_state_dict()
+    sd, _ = seeded_state_dict()
     render = neddf_b200.NeRFRender(network_config=NET_CFG, **RENDER_CFG)
     render.load_state_dict(sd)
     render.to(dev)
@@ -361,13 +606,15 @@ def main():
     h2d = n_frames * count * (S_COARSE + 1 + S_FINE + 1) * 4 + n_frames * 16 * 4
     d2h = n_frames * n_pix * 4 * 4 if rank == 0 else 0
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:  # reported at N=1 only
         threads, probe_rate = best_cpu_threads()
         cpu_rays = bounded_cpu_rays(args.cpu_rays, probe_rate, 20.0)
-        v, dt = cpu_port_rate(cpu_rays, threads)
+        keep = {}
+        v, dt = cpu_port_rate(cpu_rays, threads, keep)
         cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
                "sample": f"{cpu_rays} random rays of the same 800x800 frame ({cpu_rays * EVALS_PER_RAY} MLP evaluations, {dt:.1f} s)"}
+        parity = parity_block(render, cams[0], dev, keep)
 
     if rank == 0:
         engine = render.network_fine.resolved_engine(dev)
@@ -375,7 +622,7 @@ def main():
             "metric": "ray-samples/s (800x800x192)", "value": value, "unit": "ray-samples/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if engine == "fp32" else "f16x3-split operands, f32 accumulate (f32 on the fp32 engine)",
+            "dtype": "f32" if engine == "fp32" else "f16x3-split operands, f32 accumulate",
             "data": "synthetic", "config": workload_config(n_gpus, engine),
             "mlp_evaluations_per_s": rays_per_step * EVALS_PER_RAY / (ms_step * 1e-3),
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
@@ -384,6 +631,7 @@ def main():
                          "flop_per_evaluation": flop, "launches_timed": len(evs),
                          "kernel_share_of_step": kms / ms_total if ms_total else None},
             "cpu_baseline": cpu,
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),

@@ -49,9 +49,10 @@ extern "C" {
 #define NEDDF_UV_F32 3
 
 /* field engines */
-#define NEDDF_ENGINE_AUTO 0  /* tensor-core path when the configuration allows, else fp32 */
+#define NEDDF_ENGINE_AUTO 0  /* TC2 when the configuration allows, else TC, else fp32 */
 #define NEDDF_ENGINE_FP32 1  /* CUDA-core fp32 FMA megakernel (bit-faithful fp32 arithmetic) */
-#define NEDDF_ENGINE_TC 2    /* tcgen05 megakernel, 3-product fp16-split operands, fp32 accumulate */
+#define NEDDF_ENGINE_TC 2    /* tcgen05 megakernel, 3-product fp16-split operands, fp32 accumulate; one CTA per SM */
+#define NEDDF_ENGINE_TC2 3   /* same arithmetic, CTA pairs (tcgen05 cta_group::2): half the weight stream per sample */
 
 /* output-selection flags for neddf_field_forward* */
 #define NEDDF_OUT_FULL 0      /* everything NeDDF.forward returns, incl. fields_penalty */
@@ -117,6 +118,12 @@ int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* 
  * writes 4 SM-clock stamps per (tile, step) into d_buf[capacity] (int64): MMA phase start, MMA
  * issue done, epilogue start, epilogue done.  Pass NULL to switch it off. */
 int32_t neddf_field_set_timeline(neddf_field_t* f, int64_t* d_buf, int32_t capacity);
+
+/* Debugging aid for the tensor-core pair engine: when d_buf != NULL, cluster 0 of every following
+ * launch copies, at (its first tile, hidden step `step`), per CTA the AUX operand buffer (hi parts,
+ * 6144 words) and both accumulator halves (2 x 128 lanes x 128 columns fp32) into
+ * d_buf[2][6144 + 32768].  Pass NULL to switch it off. */
+int32_t neddf_field_set_debug_dump(neddf_field_t* f, float* d_buf, int32_t step);
 
 /* Re-pack the module's parameters into kernel layout.  d_weights[i] is the i-th layer's
  * weight, fp32 [in,out] row-major exactly as LinearGradLayer stores it

@@ -16,7 +16,7 @@ MAX_SKIPS = 8
 N_PENALTY = 6
 ACT_IDS = {"tanhExp": 0, "ReLU": 1, "LeakyReLU": 2}
 SAMPLING_IDS = {"point": 0, "cone": 1}
-ENGINE_IDS = {"auto": 0, "fp32": 1, "tc": 2}
+ENGINE_IDS = {"auto": 0, "fp32": 1, "tc": 2, "tc2": 3}
 OUT_FULL, OUT_EVAL = 0, 1
 UV_DTYPES = {torch.int64: 0, torch.int32: 1, torch.int16: 2, torch.float32: 3}
 # reference insertion order of the penalty dict (neddf/network/neddf.py:259-300)
@@ -53,6 +53,7 @@ _SIGNATURES = {
     "neddf_field_destroy": (_I32, [_P]),
     "neddf_field_resolve_engine": (_I32, [_P, _I32]),
     "neddf_field_set_timeline": (_I32, [_P, _P, _I32]),
+    "neddf_field_set_debug_dump": (_I32, [_P, _P, _I32]),
     "neddf_field_status": (_I32, [_P, C.POINTER(C.c_int32), _P]),
     "neddf_field_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P]),
     "neddf_make_rays": (_I32, [_P, _I32, _I64, _FP, _FP, _FP, _P, _P, _P]),

@@ -1,0 +1,988 @@
+// K2 (tensor-core engine, CTA pairs): the NeDDF field network as one persistent tcgen05 megakernel
+// in which the two SMs of a TPC share every weight chunk (tcgen05.mma.cta_group::2).
+//
+// Reference: NeDDF.forward (neddf/network/neddf.py:162-309), sample geometry of
+// neddf/ray/ray.py:88-194 fused into the prologue.  Arithmetic, precision scheme (fp16 hi/lo operand
+// split, three products, fp32 accumulation) and the orientation of the MMAs are those of field_tc.cu;
+// what changes is who shares what.
+//
+// Why pairs.  field_tc.cu streams the whole packed weight set (2.56 MB) from L2 for every 32-sample
+// tile; at 6.8e7 evaluations/s that is 5.9 TB/s of L2->SM traffic against a measured chip-wide ceiling
+// of ~7.2 TB/s: the single-CTA kernel cannot pass ~9e7 whatever its instruction stream looks like
+// (profiles/r02_summary.md).  Here a cluster of two CTAs processes a 64-sample tile with M = 256
+// MMAs: CTA r keeps output channels 128r..128r+127 (its half of every weight chunk, in ITS tensor
+// memory) and the B-operand rows of ITS 32 samples; the tensor cores of the pair read both halves of
+// B.  Per evaluation the weight stream is halved.
+//
+// The price is an exchange: CTA r's epilogue produces channels 128r.. for all 64 samples, and the
+// rows of the peer's 32 samples must land in the peer's shared memory (16-byte st.shared::cluster,
+// measured 19-21 B/clk per CTA in both directions at once, tools/pair_probe.py): 64 KB per layer and
+// CTA, hidden under the 6.1k-cycle MMA phase of a layer.
+//
+// Rows of a CTA's B operands (128 = 32 samples x {value, d/dx, d/dy, d/dz}):
+//     row = 64 * hs + 16 * j + s'        s = 16 hs + s' local sample, j row type
+// so that the "sample half" hs is a contiguous block of 8 row groups: one MMA covers N = 128 rows
+// = half hs of BOTH CTAs (64 rows each), accumulating into TMEM columns [128 hs, 128 hs + 128) where
+// column 64 c + 16 j + s' belongs to sample (CTA c, 16 hs + s').  The two halves ping-pong: while the
+// epilogue warps drain half 0 the tensor cores run half 1 of the same layer on the SAME weight chunks,
+// which therefore stay in the 16-stage tensor-memory ring for two passes (a chunk is freed by the
+// commit of its second pass).  When only images are wanted (no fields_penalty) the colour trunk runs
+// on the 16 value rows of each half (N = 32).
+//
+// The three narrow heads (256 -> 1, 1, 3) do not go to the tensor cores at all: the epilogue thread
+// that owns a channel multiplies its 32 fresh activations by the head weights of that channel and
+// the warp reduces over its 32 channels with a transposing butterfly (62 shuffles for 64 sums); the
+// eight partial sums per sample (4 lane quarters x 2 CTAs) meet in the shared memory of the CTA that
+// owns the sample, where one warp applies softplus / sigmoid / density / penalties.
+//
+// Per CTA: 25 warps.  warps 0-15 epilogue + prologue (lane quarter w % 4; sub-block w / 4 = (target
+// CTA, 8 samples)); warp 16 MMA issuer (leader CTA only); warps 17-24 weight loaders (L2 -> registers
+// -> tensor memory, as field_tc.cu).
+#include "tc_ptx.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace neddf {
+namespace tc2 {
+
+using namespace tc;
+
+constexpr int kPairS = 2 * kTileS;  // samples per pair tile
+constexpr int kARing = 16;          // weight chunks resident in tensor memory (16 columns each)
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kLoadWarps = 8;
+constexpr int kLoadPerQuarter = kLoadWarps / 4;
+constexpr int kThreads = kEpiThreads + 32 + kLoadWarps * 32;
+constexpr uint32_t kACol = 256;  // first TMEM column of the weight ring
+constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxSteps = kMaxHidden;
+#ifndef NEDDF_TC2_LOAD_DEPTH
+#define NEDDF_TC2_LOAD_DEPTH 3
+#endif
+#ifndef NEDDF_TC2_GROUP
+#define NEDDF_TC2_GROUP 16  // K-steps per two-pass group (<= kARing)
+#endif
+
+constexpr uint32_t kOffHHi = 0;
+constexpr uint32_t kOffHLo = kOffHHi + kHBytes;
+constexpr uint32_t kOffAuxHi = kOffHLo + kHBytes;
+constexpr uint32_t kOffAuxLo = kOffAuxHi + kAuxBytes;
+constexpr uint32_t kOffScratch = kOffAuxLo + kAuxBytes;
+
+struct Scratch {
+  float geo[kTileS][12];  // pos[3], dir[3], var[3], pad
+  HeadOut head[kTileS];
+  // head partial sums [contributor = 4 * rank + lane quarter][local sample][row type][output]
+  float hsum[8][kTileS][4][4];
+  uint64_t a_full[kARing];   // (leader) loaders of both CTAs -> MMA: chunk written to tensor memory
+  uint64_t a_empty[kARing];  // MMA -> loaders (multicast commit): chunk consumed by both passes
+  uint64_t act_ready[2];     // (leader) epilogue warps of both CTAs -> MMA: accumulator hs drained, B rows of half hs rewritten
+  uint64_t acc_ready[2];     // MMA -> epilogue warps (multicast commit): accumulator hs complete
+  uint64_t head_ready[2];    // partial head sums of this CTA's samples of half hs are in hsum
+  uint64_t norm_ready;       // (leader) both CTAs wrote the surface normals into AUX
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+constexpr uint32_t kSmemBytes = kOffScratch + sizeof(Scratch);
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct Step {
+  int aux_ksteps;  // K-steps (16) taken from AUX
+  int h_ksteps;    // K-steps taken from H
+  int aux_first;   // 1: AUX K-steps precede the H K-steps in the chunk stream, 0: they follow
+  int bias_off;    // offset into the plain-order bias array
+  int post;        // work after this step's epilogue, under the next step's MMAs: 1 = colour inputs
+                   // E0|D into AUX, 2 = next tile's prologue
+  int head;        // 1 = distance / aux heads follow this layer, 2 = colour head
+  int colour;      // layer of the colour trunk (value rows only in images-only mode)
+};
+
+struct Tc2Params {
+  FieldParams f;
+  int n_steps;
+  int chunks_per_tile;  // per CTA: one chunk per K-step
+  Step step[kMaxSteps];
+  const unsigned char* w;  // packed chunks: [(chunk, rank)] x kChunkBytes in consumption order
+  const float* bias;       // [n_hidden][256]
+  const float* w_head;     // [256][8]: ddf, aux, r, g, b, 0, 0, 0
+  int* status;
+  int eval;             // 1 = images only
+  long long* timeline;  // optional: CTA 0 writes 6 values per step
+  int timeline_cap;
+  int debug;            // NEDDF_TC2_DEBUG: 1 = issue the MMAs one asm statement each, 2 = delay the first MMA of every step
+  int col8;             // == 8: TMEM column offsets are formed at run time (see tmem column note in the epilogue)
+  float* dump;          // debugging aid: cluster 0 dumps AUX (hi) and the accumulators of (tile 0, step dump_step)
+  int dump_step;
+};
+
+// row of local sample s, type j
+__host__ __device__ __forceinline__ int row_of(int s, int j) { return 64 * (s >> 4) + 16 * j + (s & 15); }
+
+// x = hi + lo with hi, lo fp16; `amax` tracks max |hi| as packed halves (one HMNMX2 per pair: an
+// operand beyond fp16 range rounds to inf and is caught at the end of the kernel)
+__device__ __forceinline__ void split2h(float a, float b, uint32_t& hi, uint32_t& lo, __half2& amax) {
+  __half2 h = __floats2half2_rn(a, b);
+  float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+  amax = __hmax2(amax, __habs2(h));
+}
+
+// write the rows (value, Jx, Jy, Jz) of local sample s at K index k into an operand buffer pair
+__device__ __forceinline__ void store_sample2(unsigned char* hi_buf, unsigned char* lo_buf, int KC, int s, int k,
+                                              float v0, float v1, float v2, float v3, __half2& bad, int rows = 4) {
+  uint32_t h0, l0, h1, l1;
+  split2h(v0, v1, h0, l0, bad);
+  split2h(v2, v3, h1, l1, bad);
+  const uint32_t off = act_off(row_of(s, 0), k, KC);
+  const uint32_t tstride = (uint32_t)(2 * KC * 16);  // 16 rows = 2 row groups
+  *reinterpret_cast<uint16_t*>(hi_buf + off) = (uint16_t)(h0 & 0xffffu);
+  *reinterpret_cast<uint16_t*>(lo_buf + off) = (uint16_t)(l0 & 0xffffu);
+  if (rows > 1) {
+    *reinterpret_cast<uint16_t*>(hi_buf + off + tstride) = (uint16_t)(h0 >> 16);
+    *reinterpret_cast<uint16_t*>(lo_buf + off + tstride) = (uint16_t)(l0 >> 16);
+    *reinterpret_cast<uint16_t*>(hi_buf + off + 2 * tstride) = (uint16_t)(h1 & 0xffffu);
+    *reinterpret_cast<uint16_t*>(lo_buf + off + 2 * tstride) = (uint16_t)(l1 & 0xffffu);
+    *reinterpret_cast<uint16_t*>(hi_buf + off + 3 * tstride) = (uint16_t)(h1 >> 16);
+    *reinterpret_cast<uint16_t*>(lo_buf + off + 3 * tstride) = (uint16_t)(l1 >> 16);
+  }
+}
+
+// One weight chunk, one pass: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over both CTAs (M = 256); on the
+// second pass the commit that frees the ring stage in both CTAs.
+template <bool COMMIT>
+__device__ __forceinline__ void chunk_mma2_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo,
+                                                 uint32_t idesc, uint32_t accumulate, uint32_t bar) {
+  if (COMMIT) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, t;\n"
+        ".reg .b32 alo;\n"
+        ".reg .b16 mlo, mhi;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "setp.ne.b32 t, %8, 0;\n"
+        "add.u32 alo, %1, 8;\n"
+        "mov.b32 {mlo, mhi}, %9;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [alo], %2, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %3, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], mlo;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(bar), "r"(0u), "r"(1u), "r"(3u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, t;\n"
+        ".reg .b32 alo;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "setp.ne.b32 t, %7, 0;\n"
+        "add.u32 alo, %1, 8;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [alo], %2, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %3, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(0u), "r"(1u)
+        : "memory");
+  }
+}
+
+// Sum v[i] over the 32 lanes of the warp for N values per lane; afterwards lane L holds the totals of
+// indices [L * N / 32, (L + 1) * N / 32) in v[0 .. N/32).  N / 32 * 31 shuffles instead of 5 N.
+template <int N>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane) {
+#pragma unroll
+  for (int d = 16, n = N / 2; d >= 1; d >>= 1, n >>= 1) {
+    const bool upper = (lane & d) != 0;
+#pragma unroll
+    for (int t = 0; t < n; ++t) {
+      const float send = upper ? v[t] : v[t + n];
+      const float keep = upper ? v[t + n] : v[t];
+      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+    }
+  }
+}
+
+// N = 16: lane L ends with the total of index L >> 1 (both lanes of a pair hold it)
+__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int d = 16, n = 8; d >= 2; d >>= 1, n >>= 1) {
+    const bool upper = (lane & d) != 0;
+#pragma unroll
+    for (int t = 0; t < n; ++t) {
+      const float send = upper ? v[t] : v[t + n];
+      const float keep = upper ? v[t + n] : v[t];
+      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__device__ __forceinline__ void tile_geometry2(const FieldParams& p, Scratch* sc, int64_t n0, int s) {
+  float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, var[3] = {0.f, 0.f, 0.f};
+  const int64_t n = n0 + s;
+  if (n < p.n) {
+    if (p.dists) {
+      int64_t b = n / p.n_edges;
+      int j = (int)(n % p.n_edges);
+      const float* row = p.dists + b * p.n_edges;
+      float o[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        o[i] = p.ray_orig[3 * b + i];
+        dir[i] = p.ray_dir[3 * b + i];
+      }
+      sample_geometry(p.sampling_type, p.ray_radius, o, dir, row[j], far_edge(row, j, p.n_edges), pos, var);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        pos[i] = p.pos[3 * n + i];
+        dir[i] = p.dir[3 * n + i];
+        var[i] = p.var[3 * n + i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    sc->geo[s][i] = pos[i];
+    sc->geo[s][3 + i] = dir[i];
+    sc->geo[s][6 + i] = var[i];
+  }
+}
+
+// position embedding of local sample s into AUX; scaled = distance-trunk scaling (neddf.py:200-204)
+// else plain (neddf.py:205-209)
+__device__ __forceinline__ void write_pos_embedding2(const FieldParams& p, const Scratch* sc, unsigned char* aux_hi,
+                                                     unsigned char* aux_lo, int s, int sub, int nsub, bool scaled,
+                                                     __half2& bad, int rows = 4) {
+  const int half = 3 * p.embed_pos;
+  for (int idx = sub; idx < half; idx += nsub) {
+    int e = idx / 3, d = idx - 3 * e;
+    PeEntry q = pe_entry(e, sc->geo[s][d], sc->geo[s][6 + d], p.lowpass[e]);
+    float sc_ = scaled ? q.scale_s : q.scale_0;
+    float g = q.freq * sc_;
+    float js = g * q.c, jc = -g * q.s;
+    float vs[4] = {sc_ * q.s, 0.f, 0.f, 0.f}, vc[4] = {sc_ * q.c, 0.f, 0.f, 0.f};
+    vs[1 + d] = js;
+    vc[1 + d] = jc;
+    store_sample2(aux_hi, aux_lo, kAuxK, s, idx, vs[0], vs[1], vs[2], vs[3], bad, rows);
+    store_sample2(aux_hi, aux_lo, kAuxK, s, half + idx, vc[0], vc[1], vc[2], vc[3], bad, rows);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the megakernel
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_tc2_kernel(const __grid_constant__ Tc2Params P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const FieldParams& p = P.f;
+  unsigned char* h_hi = smem + kOffHHi;
+  unsigned char* h_lo = smem + kOffHLo;
+  unsigned char* aux_hi = smem + kOffAuxHi;
+  unsigned char* aux_lo = smem + kOffAuxLo;
+  Scratch* sc = reinterpret_cast<Scratch*>(smem + kOffScratch);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t cid = blockIdx.x >> 1;
+  const int64_t n_clusters = gridDim.x >> 1;
+
+  const int64_t n_tiles = (p.n + kPairS - 1) / kPairS;
+  int64_t my_tiles = 0;
+  if (cid < n_tiles) my_tiles = (n_tiles - 1 - cid) / n_clusters + 1;
+  const int64_t total_chunks = my_tiles * P.chunks_per_tile;
+
+  if (tid == 0) {
+    for (int i = 0; i < kARing; ++i) {
+      mbar_init(&sc->a_full[i], 8);   // one arrival per lane quarter and CTA
+      mbar_init(&sc->a_empty[i], 1);  // tcgen05.commit (multicast)
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&sc->act_ready[h], 2);              // one arrival per CTA (after a barrier of its epilogue threads)
+      mbar_init(&sc->acc_ready[h], 1);
+      mbar_init(&sc->head_ready[h], 2);             // one arrival per CTA: its partial sums for this CTA's samples are written
+    }
+    mbar_init(&sc->norm_ready, 2 * 32);               // every lane of the finishing warp of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) tmem_alloc2(&sc->tmem_base, kTmemCols);
+  fence_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = sc->tmem_base;
+
+  if (warp > kMmaWarp) {
+    // ===================== weight loaders: L2 -> registers -> tensor memory ======================
+    // Chunk c of this CTA = its 128 output channels x 16 K x (hi | lo); lane = channel of this warp's
+    // TMEM lane quarter, 64 contiguous bytes per lane.
+    const int quarter = warp & 3;
+    const int cpar = (warp - kMmaWarp - 1) >> 2;  // this warp loads chunks g with (g & 1) == cpar
+    const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
+    const uint4* base = reinterpret_cast<const uint4*>(P.w) + (size_t)rank * (kChunkBytes / 16) + (size_t)(32 * quarter + lane) * 4;
+    constexpr int kDepth = NEDDF_TC2_LOAD_DEPTH;
+    uint4 r[kDepth][4];
+    auto fetch = [&](int slot, int chunk) {
+      const uint4* src = base + (size_t)chunk * (2 * kChunkBytes / 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[slot][j] = __ldg(src + j);
+    };
+    // chunks_per_tile is even, so the within-tile index of chunk g has the parity of g
+    int fidx = cpar;
+    int64_t gf = cpar;
+#pragma unroll
+    for (int i = 0; i < kDepth; ++i) {
+      if (gf < total_chunks) {
+        fetch(i, fidx);
+        fidx += kLoadPerQuarter;
+        if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
+        gf += kLoadPerQuarter;
+      }
+    }
+    const uint32_t full0 = mapa_u32(smem_u32(&sc->a_full[0]), 0);  // the leader's barriers
+    int stage = cpar;
+    uint32_t par = 0;
+    bool first_pass = true;
+    int64_t g = cpar;
+    while (g < total_chunks) {
+#pragma unroll
+      for (int i = 0; i < kDepth; ++i) {
+        if (g < total_chunks) {
+          if (!first_pass) mbar_wait(&sc->a_empty[stage], par);
+          tc_fence_after();
+          const uint32_t ta = tmem + lane_addr + kACol + stage * 16;
+          const uint32_t w0[8] = {r[i][0].x, r[i][0].y, r[i][0].z, r[i][0].w, r[i][1].x, r[i][1].y, r[i][1].z, r[i][1].w};
+          const uint32_t w1[8] = {r[i][2].x, r[i][2].y, r[i][2].z, r[i][2].w, r[i][3].x, r[i][3].y, r[i][3].z, r[i][3].w};
+          tmem_st16(ta, w0, w1);
+          if (gf < total_chunks) {
+            fetch(i, fidx);
+            fidx += kLoadPerQuarter;
+            if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
+            gf += kLoadPerQuarter;
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
+          g += kLoadPerQuarter;
+          stage += kLoadPerQuarter;
+          if (stage >= kARing) {
+            stage -= kARing;
+            if (first_pass) first_pass = false;
+            else par ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (rank == 0) {
+      // ===================== MMA issuer (leader CTA; whole warp, one elected lane issues) =========
+      const uint32_t s_hhi = smem_u32(h_hi), s_ahi = smem_u32(aux_hi), s_hlo = smem_u32(h_lo), s_alo = smem_u32(aux_lo);
+      int stage = 0;          // ring position of the next chunk
+      uint32_t full_par = 0;  // parity to wait for on a_full[stage]
+      uint32_t act_phase = 0;
+      uint32_t norm_phase = 0;
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        for (int si = 0; si < P.n_steps; ++si) {
+          const Step& st = P.step[si];
+          const int tl = (int)(t * P.n_steps + si);
+          const bool stamp = P.timeline && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
+          const bool value_only = P.eval && st.colour;
+          const uint32_t idesc = value_only ? make_idesc(256, 2 * 16, 0, 1) : make_idesc(256, 2 * 64, 0, 1);
+          const int nA = st.aux_ksteps, nH = st.h_ksteps, nT = nA + nH;
+          // K-step ks of the chunk stream reads AUX or H: [0, nA) AUX then H when aux_first, else H then AUX
+          const int first_n = st.aux_first ? nA : nH;
+          // two-pass groups of at most NEDDF_TC2_GROUP K-steps (the ring holds a whole group)
+          const int n_groups = (nT + NEDDF_TC2_GROUP - 1) / NEDDF_TC2_GROUP;
+          const int g_len = (nT + n_groups - 1) / n_groups;
+          bool norm_waited = !(st.colour && st.aux_ksteps > 0);  // colour layer 0 reads the normals from AUX
+          if (stamp) P.timeline[6 * tl + 0] = clock64();
+          for (int gb = 0; gb < nT; gb += g_len) {
+            const int ge = (gb + g_len < nT) ? gb + g_len : nT;
+            const int stage0 = stage;
+            const uint32_t par0 = full_par;
+            for (int hs = 0; hs < 2; ++hs) {
+              if (gb == 0) {  // accumulator hs drained by the previous step's epilogue, B rows of half hs rewritten
+                mbar_wait(&sc->act_ready[hs], act_phase);
+                tc_fence_after();
+              }
+              const uint32_t d = tmem + 128 * hs;
+              // descriptors of half hs: 8 row groups from row group 8 hs
+              const uint64_t dba_hi = make_desc(s_ahi + hs * 8 * (kAuxK * 16), 128, kAuxK * 16);
+              const uint64_t dba_lo = make_desc(s_alo + hs * 8 * (kAuxK * 16), 128, kAuxK * 16);
+              const uint64_t dbh_hi = make_desc(s_hhi + hs * 8 * (kHK * 16), 128, kHK * 16);
+              const uint64_t dbh_lo = make_desc(s_hlo + hs * 8 * (kHK * 16), 128, kHK * 16);
+              stage = stage0;
+              full_par = par0;
+              uint32_t acc = gb > 0;
+              if ((P.debug & 2) && gb == 0) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < 200000) {}
+                tc_fence_after();
+              }
+              auto run = [&](uint64_t db_hi, uint64_t db_lo, int n) {
+                for (int i = 0; i < n; ++i) {
+                  if (P.debug & 1) {
+                    if (hs == 0) {
+                      mbar_wait(&sc->a_full[stage], full_par);
+                      tc_fence_after();
+                    }
+                    const uint32_t ta = tmem + kACol + stage * 16;
+                    mma2_f16_ts_elect(d, ta, db_hi, idesc, acc);
+                    mma2_f16_ts_elect(d, ta + 8, db_hi, idesc, 1);
+                    mma2_f16_ts_elect(d, ta, db_lo, idesc, 1);
+                    if (hs == 1) mma2_commit_elect(smem_u32(&sc->a_empty[stage]), 3);
+                  } else if (hs == 0) {
+                    mbar_wait(&sc->a_full[stage], full_par);
+                    tc_fence_after();
+                    chunk_mma2_elect<false>(d, tmem + kACol + stage * 16, db_hi, db_lo, idesc, acc, 0);
+                  } else {
+                    chunk_mma2_elect<true>(d, tmem + kACol + stage * 16, db_hi, db_lo, idesc, acc, smem_u32(&sc->a_empty[stage]));
+                  }
+                  acc = 1;
+                  db_hi += 16;  // 16 K = 256 bytes in descriptor units
+                  db_lo += 16;
+                  if (++stage == kARing) {
+                    stage = 0;
+                    full_par ^= 1;
+                  }
+                }
+              };
+              // part 1 = K-steps [0, first_n) of the stream, part 2 = the rest
+              const int b1 = gb < first_n ? gb : first_n, e1 = ge < first_n ? ge : first_n;
+              const int b2 = gb > first_n ? gb : first_n, e2 = ge > first_n ? ge : first_n;
+              const bool part1_aux = st.aux_first != 0;
+              if (b1 < e1) {
+                if (part1_aux) {
+                  run(dba_hi + b1 * 16, dba_lo + b1 * 16, e1 - b1);
+                } else {
+                  run(dbh_hi + b1 * 16, dbh_lo + b1 * 16, e1 - b1);
+                }
+              }
+              if (b2 < e2) {
+                if (!part1_aux) {
+                  if (!norm_waited) {  // the surface normals (AUX K rows n_e0 + n_d ..) of both CTAs
+                    mbar_wait(&sc->norm_ready, norm_phase);
+                    tc_fence_after();
+                    norm_phase ^= 1;
+                    norm_waited = true;
+                  }
+                  run(dba_hi + (b2 - first_n) * 16, dba_lo + (b2 - first_n) * 16, e2 - b2);
+                } else {
+                  run(dbh_hi + (b2 - first_n) * 16, dbh_lo + (b2 - first_n) * 16, e2 - b2);
+                }
+              }
+              if (ge == nT) mma2_commit_elect(smem_u32(&sc->acc_ready[hs]), 3);
+            }
+          }
+          act_phase ^= 1;
+          if (stamp) P.timeline[6 * tl + 1] = clock64();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================================================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int blk = warp >> 2;     // sub-block: samples of CTA `tc`, 8 samples `sg` of each half
+    const uint32_t tcta = (uint32_t)(blk >> 1);
+    const int sg = blk & 1;
+    const int chl = 32 * quarter + lane;     // channel within this CTA's half
+    const int ch = 128 * (int)rank + chl;    // output channel = K index of the next layer
+    const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
+    const bool remote = tcta != rank;
+    // destination operand buffers: own shared memory or the peer's
+    const uint32_t dst_hhi = mapa_u32(smem_u32(h_hi), tcta), dst_hlo = mapa_u32(smem_u32(h_lo), tcta);
+    const uint32_t dst_hsum = mapa_u32(smem_u32(&sc->hsum[4 * rank + quarter][0][0][0]), tcta);
+    const uint32_t act0 = mapa_u32(smem_u32(&sc->act_ready[0]), 0);
+    const uint32_t norm0 = mapa_u32(smem_u32(&sc->norm_ready), 0);
+    __half2 bad = __floats2half2_rn(0.f, 0.f);  // max |operand hi part| seen (fp16 range check)
+    uint32_t acc_phase = 0;
+    uint32_t head_phase = 0;
+    // head weights of this thread's channel: ddf, aux, r, g, b
+    float wh[5];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(P.w_head + 8 * ch));
+      wh[0] = a.x; wh[1] = a.y; wh[2] = a.z; wh[3] = a.w;
+      wh[4] = __ldg(P.w_head + 8 * ch + 4);
+    }
+
+    auto prologue = [&](int64_t tile) {
+      const int64_t n0 = tile * kPairS + kTileS * rank;
+      if (tid < kTileS) tile_geometry2(p, sc, n0, tid);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      const int s = tid >> 4, sub = tid & 15;
+      write_pos_embedding2(p, sc, aux_hi, aux_lo, s, sub, 16, true, bad);
+      for (int k = p.n_e0 + sub; k < 64; k += 16) store_sample2(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
+    };
+    // colour-trunk inputs E0 | D (| zero pad) into AUX (neddf.py:205-210, 243); 16 threads per sample
+    auto colour_prep = [&]() {
+      const int s = tid >> 4, sub = tid & 15;
+      const int rows = P.eval ? 1 : 4;
+      write_pos_embedding2(p, sc, aux_hi, aux_lo, s, sub, 16, false, bad, rows);
+      const int dhalf = 3 * p.embed_dir;
+      for (int idx = sub; idx < dhalf; idx += 16) {
+        int e = idx / 3, d = idx - 3 * e;
+        float sn, cs;
+        sincosf((float)(1u << e) * sc->geo[s][3 + d], &sn, &cs);
+        store_sample2(aux_hi, aux_lo, kAuxK, s, p.n_e0 + idx, sn, 0.f, 0.f, 0.f, bad, rows);
+        store_sample2(aux_hi, aux_lo, kAuxK, s, p.n_e0 + dhalf + idx, cs, 0.f, 0.f, 0.f, bad, rows);
+      }
+      for (int k = p.n_e0 + p.n_d + 3 + sub; k < kAuxK; k += 16)
+        store_sample2(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad, rows);
+    };
+    // Publish the epilogue threads' shared-memory writes (own and peer CTA) to the tensor cores and signal
+    // mbarriers (given by shared::cluster address; 0 = none).  Every thread fences its own writes towards the
+    // async proxy, a hardware named barrier orders the 512 threads, one thread arrives with release at
+    // cluster scope.  (A warp-level variant - fence, __syncwarp, lane 0 arrives - let the MMAs read operand
+    // rows before they were visible: tools/tc2_debug.py.)
+    auto cta_arrive = [&](int bar_id, uint32_t cbar0, uint32_t cbar1, uint32_t cbar2) {
+      fence_async_all();
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kEpiThreads) : "memory");
+      if (tid == 0) {
+        if (cbar0) mbar_arrive_cluster(cbar0);
+        if (cbar1) mbar_arrive_cluster(cbar1);
+        if (cbar2) mbar_arrive_cluster(cbar2);
+      }
+    };
+    const uint32_t head_ready_c0 = mapa_u32(smem_u32(&sc->head_ready[0]), 0), head_ready_c1 = mapa_u32(smem_u32(&sc->head_ready[0]), 1);
+
+    if (my_tiles > 0) {
+      prologue(cid);
+      cta_arrive(2, act0, act0 + 8, 0);
+    }
+
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int64_t tile = cid + t * n_clusters;
+      const int64_t n_own = tile * kPairS + kTileS * rank;  // first sample this CTA owns
+      for (int si = 0; si < P.n_steps; ++si) {
+        const Step& st = P.step[si];
+        const float bias = __ldg(P.bias + st.bias_off + ch);
+        const bool value_only = P.eval && st.colour;
+        const bool last = (t + 1 == my_tiles) && (si + 1 == P.n_steps);
+        const int tl = (int)(t * P.n_steps + si);
+        const bool stamp = P.timeline && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
+        for (int hs = 0; hs < 2; ++hs) {
+          if (lane == 0) mbar_wait(&sc->acc_ready[hs], acc_phase);
+          __syncwarp();
+          tc_fence_after();
+          if (stamp) P.timeline[6 * tl + 2 + 2 * hs] = clock64();
+          if (P.dump && cid == 0 && t == 0 && si == P.dump_step) {
+            // [rank][ AUX hi words 6144 | acc: hs x 128 lanes x 128 columns ]
+            float* base = P.dump + (size_t)rank * (6144 + 2 * 128 * 128);
+            if (hs == 0)
+              for (int w = tid; w < 6144; w += kEpiThreads) base[w] = __uint_as_float(reinterpret_cast<const uint32_t*>(aux_hi)[w]);
+            if (blk == 0) {  // the probe's access pattern: one warp per lane quarter, x16 loads, run-time loop
+              for (int cb = 0; cb < 8; ++cb) {
+                float v[16];
+                tmem_ld16(tmem + lane_addr + 128 * hs + cb * 16, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) base[6144 + ((size_t)hs * 128 + 32 * quarter + lane) * 128 + cb * 16 + i] = v[i];
+              }
+            }
+          }
+          // this thread: channel ch, samples (CTA tcta, 16 hs + 8 sg + i), i = 0..7
+          const uint32_t tbase = tmem + lane_addr + 128 * hs + (value_only ? 16 * tcta + 8 * sg : 64 * tcta + 8 * sg);
+          const int s0 = 16 * hs + 8 * sg;                                         // local sample of i = 0
+          const int64_t ng0 = tile * kPairS + kTileS * (int64_t)tcta + s0;         // its global index
+          float x[8], d1[8];
+          tmem_ld8(tbase, x);
+          float* save = nullptr;  // training: pre-activations [layer][sample][row type][channel]
+          if (p.save_pre) save = p.save_pre + (((size_t)st.bias_off / kWidth * p.n + ng0) * 4) * kWidth + ch;
+          if (save) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (ng0 + i < p.n) save[(size_t)i * 4 * kWidth] = x[i] + bias;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tc_hidden_act<ACT>(x[i] + bias, x[i], d1[i]);
+          uint32_t h[4], l[4];
+          uint32_t off = (uint32_t)((8 * hs + sg) * (kHK * 16) + ch * 16);  // row group of (hs, j = 0, sg)
+          const bool write_h = st.head != 2;  // the last colour layer feeds only the colour head
+          if (write_h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split2h(x[2 * i], x[2 * i + 1], h[i], l[i], bad);
+            if (remote) {
+              st_cluster_v4(dst_hhi + off, make_uint4(h[0], h[1], h[2], h[3]));
+              st_cluster_v4(dst_hlo + off, make_uint4(l[0], l[1], l[2], l[3]));
+            } else {
+              *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+          // heads: this channel's products with the head weights, reduced over the warp's 32 channels
+          // one row type at a time and parked with the owner of the sample
+          auto head_rows = [&](const float (&v)[8], int j) {
+            if (st.head == 1) {
+              float hv[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                hv[2 * i + 0] = wh[0] * v[i];
+                hv[2 * i + 1] = wh[1] * v[i];
+              }
+              warp_transpose_reduce16(hv, lane);  // lane L: sample L >> 2, output (L >> 1) & 1
+              if ((lane & 1) == 0)
+                st_cluster_f32(dst_hsum + (uint32_t)((((s0 + (lane >> 2)) * 4 + j) * 4 + ((lane >> 1) & 1)) * 4), hv[0]);
+            } else if (st.head == 2) {
+              float hv[32];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                hv[4 * i + 0] = wh[2] * v[i];
+                hv[4 * i + 1] = wh[3] * v[i];
+                hv[4 * i + 2] = wh[4] * v[i];
+                hv[4 * i + 3] = 0.f;
+              }
+              warp_transpose_reduce<32>(hv, lane);  // lane L: sample L >> 2, output L & 3
+              st_cluster_f32(dst_hsum + (uint32_t)((((s0 + (lane >> 2)) * 4 + j) * 4 + (lane & 3)) * 4), hv[0]);
+            }
+          };
+          head_rows(x, 0);
+          if (!value_only) {
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {  // Jacobian rows: G = f'(x) J (tanh_exp.py:47-48)
+              float g[8];
+              tmem_ld8(tbase + 2 * P.col8 * j, g);
+              if (save) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (ng0 + i < p.n) save[((size_t)i * 4 + j) * kWidth] = g[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] *= d1[i];
+              if (write_h) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2h(g[2 * i], g[2 * i + 1], h[i], l[i], bad);
+                off += 2 * (kHK * 16);
+                if (remote) {
+                  st_cluster_v4(dst_hhi + off, make_uint4(h[0], h[1], h[2], h[3]));
+                  st_cluster_v4(dst_hlo + off, make_uint4(l[0], l[1], l[2], l[3]));
+                } else {
+                  *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+              }
+              head_rows(g, j);
+            }
+          }
+          tc_fence_before();
+          if (stamp) P.timeline[6 * tl + 3 + 2 * hs] = clock64();
+          // accumulator hs drained, operand rows of half hs rewritten in both CTAs, head sums parked
+          if (st.head != 0) cta_arrive(2 + hs, last ? 0u : act0 + 8 * hs, head_ready_c0 + 8 * hs, head_ready_c1 + 8 * hs);
+          else if (!last) cta_arrive(2 + hs, act0 + 8 * hs, 0, 0);
+        }
+        acc_phase ^= 1;
+        // work that only feeds later steps runs here, under the next step's MMA phase; its
+        // shared-memory writes are published by the fence + arrive of the following steps
+        if (st.post == 1) colour_prep();
+        if (st.post == 2 && t + 1 < my_tiles) prologue(tile + n_clusters);
+        if (st.head != 0 && warp == 0) {
+          // ---- one warp finishes the heads for the 32 samples this CTA owns (lane = sample) ----
+          mbar_wait(&sc->head_ready[0], head_phase);
+          mbar_wait(&sc->head_ready[1], head_phase);
+          head_phase ^= 1;
+          const int s = lane;
+          if (st.head == 1) {
+            float ddf[4] = {0.f, 0.f, 0.f, 0.f}, aux[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ddf[j] += sc->hsum[c][s][j][0];
+                aux[j] += sc->hsum[c][s][j][1];
+              }
+            }
+            ddf[0] += __ldg(p.b_head + 0);
+            aux[0] += __ldg(p.b_head + 1);
+            HeadOut ho;
+            head_density(ddf, aux, p.d_near, p.aux_grad_scale, p.density_act, ho);
+            sc->head[s] = ho;
+            const int kn = p.n_e0 + p.n_d;  // normal: detached, zero Jacobian (neddf.py:243-253)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              store_sample2(aux_hi, aux_lo, kAuxK, s, kn + i, ho.normal[i], 0.f, 0.f, 0.f, bad, P.eval ? 1 : 4);
+            fence_async_all();
+            mbar_arrive_cluster(norm0);  // every lane after its own writes
+          } else {
+            // colour head (neddf.py:257) + penalties (:259-300) + outputs
+            const int64_t n = n_own + s;
+            float col[3] = {0.f, 0.f, 0.f}, colJ[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+#pragma unroll
+              for (int o = 0; o < 3; ++o) {
+                col[o] += sc->hsum[c][s][0][o];
+                if (!P.eval) {
+#pragma unroll
+                  for (int i = 0; i < 3; ++i) colJ[i][o] += sc->hsum[c][s][1 + i][o];
+                }
+              }
+            }
+            if (n < p.n) {
+              const HeadOut& ho = sc->head[s];
+#pragma unroll
+              for (int o = 0; o < 3; ++o) col[o] += __ldg(p.b_head + 2 + o);
+              if (p.distance) p.distance[n] = ho.distance;
+              if (p.density) p.density[n] = ho.density;
+              if (p.aux_grad) p.aux_grad[n] = ho.aux;
+              if (p.color) {
+                p.color[3 * n + 0] = col[0];
+                p.color[3 * n + 1] = col[1];
+                p.color[3 * n + 2] = col[2];
+              }
+              // (in images-only mode the colour Jacobian rows are not computed and no penalty is asked)
+              if (p.penalty) p.penalty[n] = field_penalty(ho, col, colJ, p.distance_range_max, p.penalty_weight);
+            }
+          }
+        }
+      }
+    }
+    {
+      const float2 m = __half22float2(bad);
+      if (!(fmaxf(m.x, m.y) < 65504.0f) && P.status) atomicOr(P.status, 4);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc2(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 [in,out] -> fp16 hi/lo chunks [(K-step, CTA rank)] in consumption order
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* w[kMaxHidden + 3];
+  const float* b[kMaxHidden + 3];
+  int k_in[kMaxHidden];
+  int aux_real[kMaxHidden];   // leading reference input channels that live in AUX (0 if none)
+  int aux_pad[kMaxHidden];    // their padded K extent in AUX
+  int aux_first[kMaxHidden];  // AUX K-steps first (1) or after the H K-steps (0)
+  int ksteps[kMaxHidden];
+  int chunk0[kMaxHidden];     // first per-CTA chunk index of the layer
+  int n_hidden;
+};
+
+__global__ void pack_hidden_kernel(PackArgs a, unsigned char* __restrict__ dst, float* __restrict__ bias) {
+  const int l = blockIdx.y;
+  const int total = a.ksteps[l] * 2 * 128 * 16;  // (kstep, rank, m, k)
+  const int aux_ks = a.aux_pad[l] / 16, h_ks = a.ksteps[l] - aux_ks;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int k = idx & 15, m = (idx >> 4) & 127, rank = (idx >> 11) & 1, ks = idx >> 12;
+    // operand-space K index of stream K-step ks: AUX part occupies [0, aux_pad), H follows
+    int ks_op = a.aux_first[l] ? ks : (ks < h_ks ? aux_ks + ks : ks - h_ks);
+    int kk = ks_op * 16 + k;
+    int row;  // reference weight row, -1 = zero padding
+    if (kk < a.aux_pad[l]) row = (kk < a.aux_real[l]) ? kk : -1;
+    else row = a.aux_real[l] + (kk - a.aux_pad[l]);
+    if (row >= a.k_in[l]) row = -1;
+    float w = (row >= 0) ? a.w[l][(size_t)row * kWidth + 128 * rank + m] : 0.f;
+    __half hi = __float2half_rn(w);
+    __half lo = __float2half_rn(w - __half2float(hi));
+    unsigned char* chunk = dst + ((size_t)(a.chunk0[l] + ks) * 2 + rank) * kChunkBytes;
+    // tensor-memory A layout: row m = lane, k pairs packed per 32-bit column; 8 hi words then 8 lo words
+    *reinterpret_cast<__half*>(chunk + m * 64 + k * 2) = hi;
+    *reinterpret_cast<__half*>(chunk + m * 64 + 32 + k * 2) = lo;
+  }
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < kWidth; c += blockDim.x) bias[l * kWidth + c] = a.b[l][c];
+}
+
+__global__ void pack_heads_kernel(PackArgs a, float* __restrict__ w_head) {
+  const int nh = a.n_hidden;
+  for (int k = threadIdx.x; k < kWidth; k += blockDim.x) {
+    w_head[8 * k + 0] = a.w[nh + 0][k];
+    w_head[8 * k + 1] = a.w[nh + 1][k];
+    w_head[8 * k + 2] = a.w[nh + 2][3 * k + 0];
+    w_head[8 * k + 3] = a.w[nh + 2][3 * k + 1];
+    w_head[8 * k + 4] = a.w[nh + 2][3 * k + 2];
+    w_head[8 * k + 5] = 0.f;
+    w_head[8 * k + 6] = 0.f;
+    w_head[8 * k + 7] = 0.f;
+  }
+}
+
+struct Storage {
+  unsigned char* d_w = nullptr;
+  float* d_bias = nullptr;
+  float* d_w_head = nullptr;
+  int* d_status = nullptr;
+  int n_steps = 0;
+  int chunks_per_tile = 0;
+  Step step[kMaxSteps];
+  PackArgs pack;
+  long long* timeline = nullptr;
+  int timeline_cap = 0;
+  float* dump = nullptr;
+  int dump_step = 0;
+};
+
+}  // namespace tc2
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool tc2_is_skip_layer(const neddf_field* f, int l) {
+  for (int i = 0; i < f->cfg.n_skips; ++i)
+    if (f->cfg.skips[i] == l - 1) return true;
+  return false;
+}
+
+bool tc2_supported(const neddf_field* f) {
+  // AUX holds 64 K (position embedding of the distance trunk) / 96 K (colour inputs E0 | D | n)
+  const int n_e0 = 6 * f->cfg.embed_pos_rank, off_h = n_e0 + 6 * f->cfg.embed_dir_rank + 3;
+  return n_e0 <= 64 && off_h <= tc::kAuxK && f->cfg.ddf_layer_width == kWidth && f->cfg.col_layer_width == kWidth;
+}
+
+static int32_t tc2_ensure(neddf_field* f) {
+  if (f->tc2) return NEDDF_OK;
+  tc2::Storage* S = new tc2::Storage();
+  const int n_hidden = f->n_ddf + f->n_col;
+  int chunk = 0;
+  std::memset(&S->pack, 0, sizeof(S->pack));
+  S->pack.n_hidden = n_hidden;
+  int last_aux = 0;
+  for (int l = 0; l < n_hidden; ++l) {
+    int aux_real = 0, aux_pad = 0, h_k = 0, aux_first = 1;
+    if (l == 0) { aux_real = f->proto.n_e0; aux_pad = 64; }
+    else if (l < f->n_ddf) { if (tc2_is_skip_layer(f, l)) { aux_real = f->proto.n_e0; aux_pad = 64; } h_k = kWidth; }
+    else if (l == f->n_ddf) { aux_real = f->proto.off_h; aux_pad = tc::kAuxK; h_k = kWidth; aux_first = 0; }
+    else h_k = kWidth;
+    tc2::Step& st = S->step[l];
+    st.aux_ksteps = aux_pad / 16;
+    st.h_ksteps = h_k / 16;
+    st.aux_first = aux_first;
+    st.bias_off = l * kWidth;
+    st.post = 0;
+    st.head = (l == f->n_ddf - 1) ? 1 : (l == n_hidden - 1) ? 2 : 0;
+    st.colour = l >= f->n_ddf;
+    if (l < f->n_ddf && aux_pad > 0) last_aux = l;
+    S->pack.k_in[l] = f->shape_in[l];
+    S->pack.aux_real[l] = aux_real;
+    S->pack.aux_pad[l] = aux_pad;
+    S->pack.aux_first[l] = aux_first;
+    S->pack.ksteps[l] = st.aux_ksteps + st.h_ksteps;
+    S->pack.chunk0[l] = chunk;
+    chunk += S->pack.ksteps[l];
+  }
+  S->n_steps = n_hidden;
+  S->chunks_per_tile = chunk;
+  // AUX holds E_s until the last trunk layer that reads it; after that layer's epilogue the colour
+  // inputs E0|D are written while later trunk layers run.  After the first colour layer's epilogue
+  // AUX is dead again: the next tile's prologue goes there.
+  S->step[last_aux].post = 1;
+  S->step[f->n_ddf].post = 2;
+  if (cudaMalloc(&S->d_w, (size_t)chunk * 2 * tc::kChunkBytes) != cudaSuccess ||
+      cudaMalloc(&S->d_bias, (size_t)n_hidden * kWidth * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&S->d_w_head, (size_t)kWidth * 8 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess) {
+    cudaFree(S->d_w); cudaFree(S->d_bias); cudaFree(S->d_w_head); cudaFree(S->d_status);
+    delete S;
+    return fail(NEDDF_E_CUDA, "tensor-core pair engine: cudaMalloc failed");
+  }
+  cudaMemset(S->d_status, 0, sizeof(int));
+  f->tc2 = S;
+  return NEDDF_OK;
+}
+
+void tc2_destroy(neddf_field* f) {
+  if (!f->tc2) return;
+  tc2::Storage* S = static_cast<tc2::Storage*>(f->tc2);
+  cudaFree(S->d_w);
+  cudaFree(S->d_bias);
+  cudaFree(S->d_w_head);
+  cudaFree(S->d_status);
+  delete S;
+  f->tc2 = nullptr;
+}
+
+int32_t tc2_pack_weights(neddf_field* f, const float* const* d_w, const float* const* d_b, cudaStream_t s) {
+  int32_t rc = tc2_ensure(f);
+  if (rc != NEDDF_OK) return rc;
+  tc2::Storage* S = static_cast<tc2::Storage*>(f->tc2);
+  tc2::PackArgs a = S->pack;
+  const int n_hidden = f->n_ddf + f->n_col;
+  for (int l = 0; l < n_hidden + 3; ++l) {
+    a.w[l] = d_w[l];
+    a.b[l] = d_b[l];
+  }
+  tc2::pack_hidden_kernel<<<dim3(64, n_hidden), 256, 0, s>>>(a, S->d_w, S->d_bias);
+  NEDDF_LAUNCH_CHECK();
+  tc2::pack_heads_kernel<<<1, 256, 0, s>>>(a, S->d_w_head);
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}
+
+int32_t launch_field_tc2(const neddf_field* f, FieldParams& p, int flags, cudaStream_t s) {
+  tc2::Storage* S = static_cast<tc2::Storage*>(f->tc2);
+  if (!S) return fail(NEDDF_E_INVALID, "tensor-core pair engine: weights were never packed");
+  tc2::Tc2Params P;
+  P.f = p;
+  P.n_steps = S->n_steps;
+  P.chunks_per_tile = S->chunks_per_tile;
+  for (int i = 0; i < S->n_steps; ++i) P.step[i] = S->step[i];
+  P.w = S->d_w;
+  P.bias = S->d_bias;
+  P.w_head = S->d_w_head;
+  P.status = S->d_status;
+  P.eval = (flags == NEDDF_OUT_EVAL && p.penalty == nullptr && p.save_pre == nullptr) ? 1 : 0;
+  P.timeline = S->timeline;
+  P.timeline_cap = S->timeline_cap;
+  P.col8 = 8;
+  P.debug = 0;
+  if (const char* e = std::getenv("NEDDF_TC2_DEBUG")) P.debug = std::atoi(e);
+  P.dump = S->dump;
+  P.dump_step = S->dump_step;
+  int64_t n_tiles = (p.n + tc2::kPairS - 1) / tc2::kPairS;
+  int grid = 2 * (int)std::min<int64_t>(n_tiles, sm_count() / 2);
+  auto launch = [&](auto kern) -> int32_t {
+    NEDDF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemBytes));
+    kern<<<grid, tc2::kThreads, tc2::kSmemBytes, s>>>(P);
+    NEDDF_LAUNCH_CHECK();
+    return NEDDF_OK;
+  };
+  switch (p.hidden_act) {
+    case NEDDF_ACT_TANHEXP: return launch(tc2::field_tc2_kernel<NEDDF_ACT_TANHEXP>);
+    case NEDDF_ACT_RELU: return launch(tc2::field_tc2_kernel<NEDDF_ACT_RELU>);
+    case NEDDF_ACT_LEAKYRELU: return launch(tc2::field_tc2_kernel<NEDDF_ACT_LEAKYRELU>);
+  }
+  return fail(NEDDF_E_INVALID, "tensor-core pair engine: unknown activation");
+}
+
+int32_t tc2_set_timeline(neddf_field* f, long long* d_buf, int cap) {
+  int32_t rc = tc2_ensure(f);
+  if (rc != NEDDF_OK) return rc;
+  tc2::Storage* S = static_cast<tc2::Storage*>(f->tc2);
+  S->timeline = d_buf;
+  S->timeline_cap = d_buf ? cap : 0;
+  return NEDDF_OK;
+}
+
+int32_t tc2_set_dump(neddf_field* f, float* d_buf, int step) {
+  int32_t rc = tc2_ensure(f);
+  if (rc != NEDDF_OK) return rc;
+  tc2::Storage* S = static_cast<tc2::Storage*>(f->tc2);
+  S->dump = d_buf;
+  S->dump_step = step;
+  return NEDDF_OK;
+}
+
+int32_t tc2_read_status(const neddf_field* f, int* out, cudaStream_t s) {
+  tc2::Storage* S = static_cast<tc2::Storage*>(f->tc2);
+  *out = 0;
+  if (!S) return NEDDF_OK;
+  NEDDF_CUDA_CHECK(cudaMemcpyAsync(out, S->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  NEDDF_CUDA_CHECK(cudaStreamSynchronize(s));
+  NEDDF_CUDA_CHECK(cudaMemsetAsync(S->d_status, 0, sizeof(int), s));
+  return NEDDF_OK;
+}
+
+}  // namespace neddf

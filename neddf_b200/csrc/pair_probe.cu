@@ -8,7 +8,7 @@
 //       the multicast commit and the accumulator layout; also times `reps` repetitions.
 //   neddf_dsmem_bench      : 16-byte st.shared::cluster stores into the peer CTA's shared memory
 //       (the activation exchange of the pair kernel), bytes per cycle.
-#include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "tc_ptx.cuh"
 
@@ -17,10 +17,10 @@ namespace tc {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     tc_pair_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int n, int k,
-                            float* __restrict__ C, long long* __restrict__ cyc, int reps) {
+                            float* __restrict__ C, long long* __restrict__ cyc, int reps, int kc, int row0, int rmode, int c8, int boff) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* h_hi = smem;
-  unsigned char* h_lo = smem + kHBytes;
+  unsigned char* h_hi = smem + boff;
+  unsigned char* h_lo = smem + boff + 32768;
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -30,8 +30,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     int kk = idx % k, r = idx / k;
     float b = B[(size_t)(nh * rank + r) * k + kk];
     __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
-    *reinterpret_cast<__half*>(h_hi + act_off(r, kk, kHK)) = hi;
-    *reinterpret_cast<__half*>(h_lo + act_off(r, kk, kHK)) = lo;
+    *reinterpret_cast<__half*>(h_hi + act_off(row0 + r, kk, kc)) = hi;
+    *reinterpret_cast<__half*>(h_lo + act_off(row0 + r, kk, kc)) = lo;
   }
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -67,7 +67,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       for (int ks = 0; ks < k / 16; ++ks) {
-        const uint64_t db_hi = make_desc(s_hhi + ks * 256, 128, kHK * 16), db_lo = make_desc(s_hlo + ks * 256, 128, kHK * 16);
+        const uint32_t roff = (uint32_t)(row0 >> 3) * (kc * 16);
+        const uint64_t db_hi = make_desc(s_hhi + roff + ks * 256, 128, kc * 16), db_lo = make_desc(s_hlo + roff + ks * 256, 128, kc * 16);
         const uint32_t ta = tmem + 256 + ks * 16;
         mma2_f16_ts_elect(tmem, ta, db_hi, idesc, (r | ks) > 0);
         mma2_f16_ts_elect(tmem, ta + 8, db_hi, idesc, 1);
@@ -83,11 +84,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
   }
   __syncthreads();
   tc_fence_after();
-  for (int cb = 0; cb < n / 16; ++cb) {
-    float v[16];
-    tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + cb * 16, v);
+  if (rmode == 0) {
+    for (int cb = 0; cb < n / 16; ++cb) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + cb * 16, v);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) C[(size_t)(128 * rank + m) * n + cb * 16 + i] = v[i] / (float)reps;
+      for (int i = 0; i < 16; ++i) C[(size_t)(128 * rank + m) * n + cb * 16 + i] = v[i] / (float)reps;
+    }
+  } else if (rmode == 1) {
+    // x8 loads, compile-time column offsets inside 32-column blocks (ptxas folds them into the LDTM immediate)
+    for (int cb = 0; cb < n / 32; ++cb) {
+      const uint32_t base = tmem + ((uint32_t)(32 * warp) << 16) + cb * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+        tmem_ld8(base + 8 * q, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) C[(size_t)(128 * rank + m) * n + cb * 32 + 8 * q + i] = v[i] / (float)reps;
+      }
+    }
+  } else {
+    // x8 loads, run-time column offsets (c8 == 8, a kernel argument)
+    for (int cb = 0; cb < n / 32; ++cb) {
+      const uint32_t base = tmem + ((uint32_t)(32 * warp) << 16) + cb * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+        tmem_ld8(base + c8 * q, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) C[(size_t)(128 * rank + m) * n + cb * 32 + 8 * q + i] = v[i] / (float)reps;
+      }
+    }
   }
   tc_fence_before();
   cluster_sync_all();
@@ -136,12 +163,24 @@ using namespace neddf;
 
 extern "C" int32_t neddf_tc_pair_selftest(const float* d_a, const float* d_b, int32_t n, int32_t k, float* d_c,
                                           int64_t* d_cycles, int32_t reps, void* stream) {
+  // probe variants: NEDDF_PAIR_KC = K capacity of the B buffer (row-group stride kc*16 bytes),
+  // NEDDF_PAIR_ROW0 = first row of the B tile inside the buffer (multiple of 8)
+  int kc = tc::kHK, row0 = 0;
+  if (const char* e = std::getenv("NEDDF_PAIR_KC")) kc = std::atoi(e);
+  if (const char* e = std::getenv("NEDDF_PAIR_ROW0")) row0 = std::atoi(e);
+  int rmode = 0;  // NEDDF_PAIR_READ: 0 = x16 loads, 1 = x8 loads with immediate column offsets, 2 = x8 with run-time offsets
+  if (const char* e = std::getenv("NEDDF_PAIR_READ")) rmode = std::atoi(e);
+  int boff = 0;  // NEDDF_PAIR_BASE: byte offset of the B buffers inside the dynamic shared memory (hi, lo 32 KB apart)
+  if (const char* e = std::getenv("NEDDF_PAIR_BASE")) boff = std::atoi(e);
+  if (boff < 0 || boff > 131072 || (boff % 1024) != 0 || (size_t)(row0 + n / 2 + 7) / 8 * kc * 16 > 32768)
+    return fail(NEDDF_E_INVALID, "neddf_tc_pair_selftest: bad NEDDF_PAIR_BASE / tile does not fit 32 KB");
+  if (kc < k || kc > 256 || (row0 % 8) != 0 || row0 + n / 2 > 128) return fail(NEDDF_E_INVALID, "neddf_tc_pair_selftest: bad probe variant");
   if (k < 16 || k > 256 || (k % 16) != 0 || reps < 1 || n < 32 || n > 256 || (n % 32) != 0)
     return fail(NEDDF_E_INVALID, "neddf_tc_pair_selftest: need k in [16,256] (multiple of 16), n in [32,256] (multiple of 32)");
   if (!d_a || !d_b || !d_c) return fail(NEDDF_E_INVALID, "neddf_tc_pair_selftest: NULL pointer");
-  size_t smem = 2 * tc::kHBytes;
+  size_t smem = 131072 + 65536;
   NEDDF_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::tc_pair_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(d_a, d_b, n, k, d_c, reinterpret_cast<long long*>(d_cycles), reps);
+  tc::tc_pair_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(d_a, d_b, n, k, d_c, reinterpret_cast<long long*>(d_cycles), reps, kc, row0, rmode, 8, boff);
   NEDDF_LAUNCH_CHECK();
   return NEDDF_OK;
 }

@@ -242,7 +242,7 @@ class NeDDF(BaseNeuralField):
         self.penalty_weight = {k: float(v) for k, v in dict(penalty_weight).items()}
 
         # kernel-side state
-        self.engine = "auto"          # "auto" | "fp32" | "tc"
+        self.engine = "auto"          # "auto" | "fp32" | "tc" | "tc2"
         self._handle = None
         self._handle_device = None
         self._packed_key = None
@@ -252,7 +252,7 @@ class NeDDF(BaseNeuralField):
         """Engine that will actually run for ``self.engine`` ("fp32" or "tc")."""
         h = self._field(torch.device(device) if device is not None else self.device)
         rc = L.check(L.lib().neddf_field_resolve_engine(h, L.ENGINE_IDS[self.engine]), "resolve_engine")
-        return {1: "fp32", 2: "tc"}[rc]
+        return {1: "fp32", 2: "tc", 3: "tc2"}[rc]
 
     # ------------------------------------------------------------------ kernel plumbing --
     def _ordered_layers(self) -> List[LinearGradLayer]:

@@ -39,3 +39,20 @@ def test_workload_constants_match_baseline(repo_root):
     assert bench.W == 800 and bench.H == 800 and bench.NOMINAL_PER_RAY == 192
     assert bench.EVALS_PER_RAY == 65 + 194  # coarse edges + merged fine edges (nerf_render.py:118-156)
     assert "ray-samples/s" in json.dumps(base)
+
+
+def test_product_weights_equal_the_oracle_stream(repo_root):
+    """bench.py builds its weights without test infrastructure; the CPU legs (oracle) must see the same
+    numbers: the product-side generator stream equals oracle.init_params."""
+    sys.path.insert(0, repo_root)
+    import torch
+
+    import bench
+    from oracle import neddf_oracle as orc
+    p = bench.seeded_params()
+    ref = orc.init_params(orc.FieldConfig.from_dict(bench.NET_CFG), bench.WEIGHT_SEED, bias_std=0.05)
+    assert list(p) == list(ref)
+    assert all(torch.equal(p[k], ref[k]) for k in ref)
+    src = open(os.path.join(repo_root, "bench.py")).read()
+    main_src = src[src.index("def main():"):]
+    assert "oracle" not in main_src.split("cpu_port_rate")[0]  # product arm set-up imports no oracle

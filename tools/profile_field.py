@@ -8,7 +8,7 @@ import neddf_b200
 engine = sys.argv[1] if len(sys.argv) > 1 else "auto"
 n_rays = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 dev = torch.device("cuda:0")
-sd, _, _ = bench.seeded_state_dict()
+sd, _ = bench.seeded_state_dict()
 render = neddf_b200.NeRFRender(network_config=bench.NET_CFG, **bench.RENDER_CFG)
 render.load_state_dict(sd); render.to(dev); render.set_iter(-1); render.set_engine(engine)
 R, T, calib = bench.synthetic_pose(0)

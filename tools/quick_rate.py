@@ -9,7 +9,7 @@ n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 engine = sys.argv[3] if len(sys.argv) > 3 else "tc"
 dev = torch.device("cuda:0")
-sd, _, _ = bench.seeded_state_dict()
+sd, _ = bench.seeded_state_dict()
 R, T, calib = bench.synthetic_pose(0)
 cam = neddf_b200.Camera.from_matrix(neddf_b200.PinholeCalib(calib), R, T).to(dev); cam.update_transform()
 first = (bench.H // 2) * bench.W

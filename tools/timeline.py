@@ -12,7 +12,7 @@ from neddf_b200 import _lib as L
 
 modes = [int(a) for a in sys.argv[1:]] or [0]
 dev = torch.device("cuda:0")
-sd, _, _ = bench.seeded_state_dict()
+sd, _ = bench.seeded_state_dict()
 render = neddf_b200.NeRFRender(network_config=bench.NET_CFG, **bench.RENDER_CFG)
 render.load_state_dict(sd); render.to(dev); render.set_iter(-1); render.set_engine("tc")
 render.check_nan = False

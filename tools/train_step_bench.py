@@ -7,7 +7,7 @@ import bench, neddf_b200
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 dev = torch.device("cuda:0")
-sd, _, _ = bench.seeded_state_dict()
+sd, _ = bench.seeded_state_dict()
 render = neddf_b200.NeRFRender(network_config=bench.NET_CFG, **bench.RENDER_CFG)
 render.load_state_dict(sd); render.to(dev); render.check_nan = False
 R, T, calib = bench.synthetic_pose(0)
