@@ -292,6 +292,10 @@ int32_t neddf_tc_pair_selftest(const float* d_a, const float* d_b, int32_t n, in
 int32_t neddf_dsmem_bench(int32_t mode, int32_t reps, int32_t bytes, int32_t n_clusters, int64_t* d_cycles,
                           void* stream);
 
+/* tcgen05.cp layout probe (profiling / bring-up aid): one 128x256b shared-memory -> tensor-memory copy of
+ * the 16-bit pattern value[i] = i with descriptor strides (lbo, sbo); d_out[128 lanes][8 columns]. */
+int32_t neddf_tc_cp_probe(int32_t lbo, int32_t sbo, uint32_t* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "neddf_tc_selftest_ts": (_I32, [_P, _P, _I32, _P, _P, _I32, _P]),
     "neddf_tc_selftest": (_I32, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "neddf_tc_pair_selftest": (_I32, [_P, _P, _I32, _I32, _P, _P, _I32, _P]),
+    "neddf_tc_cp_probe": (_I32, [_I32, _I32, _P, _P]),
     "neddf_dsmem_bench": (_I32, [_I32, _I32, _I32, _I32, _P, _P]),
 }
 

@@ -35,9 +35,17 @@
 // eight partial sums per sample (4 lane quarters x 2 CTAs) meet in the shared memory of the CTA that
 // owns the sample, where one warp applies softplus / sigmoid / density / penalties.
 //
-// Per CTA: 25 warps.  warps 0-15 epilogue + prologue (lane quarter w % 4; sub-block w / 4 = (target
-// CTA, 8 samples)); warp 16 MMA issuer (leader CTA only); warps 17-24 weight loaders (L2 -> registers
-// -> tensor memory, as field_tc.cu).
+// Weights.  A chunk = two K-steps of this CTA's 128 channels (16 KB: per K-step 4 KB hi | 4 KB lo in
+// the K-major core-matrix layout).  One thread per CTA streams the chunks from L2 into a two-stage
+// shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); one thread of the
+// leader moves each staged chunk of BOTH CTAs into the tensor-memory ring (8 stages x 32 columns) with
+// four tcgen05.cp.cta_group::2.128x256b and commits; the MMAs take A from tensor memory at the 64-cycle
+// rate.  (Round-2 first version: eight loader warps per CTA went L2 -> registers -> tcgen05.st as in
+// field_tc.cu; their ~1400-cycle period per chunk and warp was the bottleneck - tools/loader_timeline.py.)
+//
+// Per CTA: 19 warps.  warps 0-15 epilogue + prologue (lane quarter w % 4; sub-block w / 4 = (target
+// CTA, 8 samples)); warp 16 MMA issuer (leader CTA only); warp 17 TMA producer; warp 18 tcgen05.cp
+// issuer (leader) / forwarder of "my chunk landed" to the leader (peer).
 #include "tc_ptx.cuh"
 
 #include <algorithm>
@@ -51,36 +59,40 @@ namespace tc2 {
 using namespace tc;
 
 constexpr int kPairS = 2 * kTileS;  // samples per pair tile
-constexpr int kARing = 16;          // weight chunks resident in tensor memory (16 columns each)
+constexpr int kChunkK = 2;                            // K-steps per weight chunk
+constexpr int kWChunkBytes = kChunkK * kChunkBytes;   // 16 KB per CTA and chunk
+constexpr int kARing = 8;                             // chunks resident in tensor memory (32 columns each)
+constexpr int kSStages = 2;                           // shared-memory staging ring of the TMA copies
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;
-constexpr int kLoadWarps = 8;
-constexpr int kLoadPerQuarter = kLoadWarps / 4;
-constexpr int kThreads = kEpiThreads + 32 + kLoadWarps * 32;
+constexpr int kTmaWarp = kEpiWarps + 1;
+constexpr int kCpWarp = kEpiWarps + 2;
+constexpr int kThreads = kEpiThreads + 3 * 32;
 constexpr uint32_t kACol = 256;  // first TMEM column of the weight ring
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxSteps = kMaxHidden;
-#ifndef NEDDF_TC2_LOAD_DEPTH
-#define NEDDF_TC2_LOAD_DEPTH 3
-#endif
 #ifndef NEDDF_TC2_GROUP
-#define NEDDF_TC2_GROUP 16  // K-steps per two-pass group (<= kARing)
+#define NEDDF_TC2_GROUP 8  // chunks per two-pass group (<= kARing)
 #endif
 
 constexpr uint32_t kOffHHi = 0;
 constexpr uint32_t kOffHLo = kOffHHi + kHBytes;
 constexpr uint32_t kOffAuxHi = kOffHLo + kHBytes;
 constexpr uint32_t kOffAuxLo = kOffAuxHi + kAuxBytes;
-constexpr uint32_t kOffScratch = kOffAuxLo + kAuxBytes;
+constexpr uint32_t kOffStage = kOffAuxLo + kAuxBytes;
+constexpr uint32_t kOffScratch = kOffStage + kSStages * kWChunkBytes;
 
 struct Scratch {
   float geo[kTileS][12];  // pos[3], dir[3], var[3], pad
   HeadOut head[kTileS];
-  // head partial sums [contributor = 4 * rank + lane quarter][local sample][row type][output]
-  float hsum[8][kTileS][4][4];
-  uint64_t a_full[kARing];   // (leader) loaders of both CTAs -> MMA: chunk written to tensor memory
-  uint64_t a_empty[kARing];  // MMA -> loaders (multicast commit): chunk consumed by both passes
+  // head partial sums [contributor = 4 * rank + lane quarter][local sample][3 * row type + output]
+  float hsum[8][kTileS][12];
+  uint64_t s_full[kSStages];     // TMA -> (this CTA's) cp issuer / forwarder: chunk landed in shared memory
+  uint64_t s_empty[kSStages];    // tcgen05.commit (multicast) -> TMA producers: staged chunk copied to tensor memory
+  uint64_t peer_full[kSStages];  // (leader) the peer's chunk landed in the peer's shared memory
+  uint64_t a_full[kARing];       // (leader) tcgen05.commit -> MMA: chunk of both CTAs is in tensor memory
+  uint64_t a_empty[kARing];      // (leader) tcgen05.commit -> cp issuer: chunk consumed by both passes
   uint64_t act_ready[2];     // (leader) epilogue warps of both CTAs -> MMA: accumulator hs drained, B rows of half hs rewritten
   uint64_t acc_ready[2];     // MMA -> epilogue warps (multicast commit): accumulator hs complete
   uint64_t head_ready[2];    // partial head sums of this CTA's samples of half hs are in hsum
@@ -105,16 +117,19 @@ struct Step {
 struct Tc2Params {
   FieldParams f;
   int n_steps;
-  int chunks_per_tile;  // per CTA: one chunk per K-step
+  int chunks_per_tile;  // per CTA: one chunk per two K-steps
   Step step[kMaxSteps];
-  const unsigned char* w;  // packed chunks: [(chunk, rank)] x kChunkBytes in consumption order
+  const unsigned char* w;  // packed chunks: [(chunk, rank)] x kWChunkBytes in consumption order
   const float* bias;       // [n_hidden][256]
   const float* w_head;     // [256][8]: ddf, aux, r, g, b, 0, 0, 0
   int* status;
   int eval;             // 1 = images only
   long long* timeline;  // optional: CTA 0 writes 6 values per step
   int timeline_cap;
-  int debug;            // NEDDF_TC2_DEBUG: 1 = issue the MMAs one asm statement each, 2 = delay the first MMA of every step
+  int debug;            // NEDDF_TC2_DEBUG (timing experiments; 4..64 make the results garbage): 1 = one asm statement per MMA,
+                        // 2 = delay the first MMA of every step, 4 = MMA warp does not wait for weight chunks, 8 = loaders skip
+                        // the L2 reads, 16 = epilogue skips its math and stores, 32 = no remote stores (peer rows stay stale),
+                        // 64 = no MMAs
   int col8;             // == 8: TMEM column offsets are formed at run time (see tmem column note in the epilogue)
   float* dump;          // debugging aid: cluster 0 dumps AUX (hi) and the accumulators of (tile 0, step dump_step)
   int dump_step;
@@ -154,8 +169,10 @@ __device__ __forceinline__ void store_sample2(unsigned char* hi_buf, unsigned ch
   }
 }
 
-// One weight chunk, one pass: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over both CTAs (M = 256); on the
-// second pass the commit that frees the ring stage in both CTAs.
+// One weight chunk (two K-steps), one pass: for each K-step D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over
+// both CTAs (M = 256).  A of K-step u at tensor-memory columns a + 16u (hi) / a + 16u + 8 (lo); the B
+// descriptors advance by 16 (256 bytes) per K-step.  On the second pass the commit that frees the ring stage
+// (the leader's barrier `bar`).
 template <bool COMMIT>
 __device__ __forceinline__ void chunk_mma2_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo,
                                                  uint32_t idesc, uint32_t accumulate, uint32_t bar) {
@@ -163,36 +180,76 @@ __device__ __forceinline__ void chunk_mma2_elect(uint32_t d_tmem, uint32_t a_tme
     asm volatile(
         "{\n"
         ".reg .pred p, q, t;\n"
-        ".reg .b32 alo;\n"
+        ".reg .b32 a1, a2, a3;\n"
+        ".reg .b64 bh1, bl1;\n"
         ".reg .b16 mlo, mhi;\n"
         "elect.sync _|q, 0xffffffff;\n"
         "setp.ne.b32 p, %5, 0;\n"
         "setp.ne.b32 t, %8, 0;\n"
-        "add.u32 alo, %1, 8;\n"
+        "add.u32 a1, %1, 8;\n"
+        "add.u32 a2, %1, 16;\n"
+        "add.u32 a3, %1, 24;\n"
+        "add.u64 bh1, %2, 16;\n"
+        "add.u64 bl1, %3, 16;\n"
         "mov.b32 {mlo, mhi}, %9;\n"
         "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n"
-        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [alo], %2, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a1], %2, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
         "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %3, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], bh1, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a3], bh1, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], bl1, %4, {%7, %7, %7, %7, %7, %7, %7, %7}, t;\n"
         "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], mlo;\n"
         "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(bar), "r"(0u), "r"(1u), "r"(3u)
+        "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(bar), "r"(0u), "r"(1u), "r"(1u)
         : "memory");
   } else {
     asm volatile(
         "{\n"
         ".reg .pred p, q, t;\n"
-        ".reg .b32 alo;\n"
+        ".reg .b32 a1, a2, a3;\n"
+        ".reg .b64 bh1, bl1;\n"
         "elect.sync _|q, 0xffffffff;\n"
         "setp.ne.b32 p, %5, 0;\n"
         "setp.ne.b32 t, %7, 0;\n"
-        "add.u32 alo, %1, 8;\n"
+        "add.u32 a1, %1, 8;\n"
+        "add.u32 a2, %1, 16;\n"
+        "add.u32 a3, %1, 24;\n"
+        "add.u64 bh1, %2, 16;\n"
+        "add.u64 bl1, %3, 16;\n"
         "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n"
-        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [alo], %2, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a1], %2, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
         "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %3, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], bh1, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a3], bh1, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], bl1, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, t;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(0u), "r"(1u)
         : "memory");
   }
+}
+
+// shared memory -> tensor memory in both CTAs: 128 lanes x 8 columns from a 4 KB K-major core-matrix block
+__device__ __forceinline__ void tmem_cp2_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+// commit without elect (a single thread issues): all prior async tcgen05 operations of this thread
+__device__ __forceinline__ void mma2_commit(uint32_t bar, uint32_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 lo, hi;\n"
+      "mov.b32 {lo, hi}, %1;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], lo;\n"
+      "}\n" ::"r"(bar),
+      "r"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // Sum v[i] over the 32 lanes of the warp for N values per lane; afterwards lane L holds the totals of
@@ -304,9 +361,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
   const int64_t total_chunks = my_tiles * P.chunks_per_tile;
 
   if (tid == 0) {
+    for (int i = 0; i < kSStages; ++i) {
+      mbar_init(&sc->s_full[i], 1);     // expect_tx arrival of the producer + the TMA bytes
+      mbar_init(&sc->s_empty[i], 1);    // tcgen05.commit (multicast)
+      mbar_init(&sc->peer_full[i], 1);  // the peer's forwarder
+    }
     for (int i = 0; i < kARing; ++i) {
-      mbar_init(&sc->a_full[i], 8);   // one arrival per lane quarter and CTA
-      mbar_init(&sc->a_empty[i], 1);  // tcgen05.commit (multicast)
+      mbar_init(&sc->a_full[i], 1);   // tcgen05.commit of the copies
+      mbar_init(&sc->a_empty[i], 1);  // tcgen05.commit of the second MMA pass
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&sc->act_ready[h], 2);              // one arrival per CTA (after a barrier of its epilogue threads)
@@ -323,64 +385,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
   tc_fence_after();
   const uint32_t tmem = sc->tmem_base;
 
-  if (warp > kMmaWarp) {
-    // ===================== weight loaders: L2 -> registers -> tensor memory ======================
-    // Chunk c of this CTA = its 128 output channels x 16 K x (hi | lo); lane = channel of this warp's
-    // TMEM lane quarter, 64 contiguous bytes per lane.
-    const int quarter = warp & 3;
-    const int cpar = (warp - kMmaWarp - 1) >> 2;  // this warp loads chunks g with (g & 1) == cpar
-    const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
-    const uint4* base = reinterpret_cast<const uint4*>(P.w) + (size_t)rank * (kChunkBytes / 16) + (size_t)(32 * quarter + lane) * 4;
-    constexpr int kDepth = NEDDF_TC2_LOAD_DEPTH;
-    uint4 r[kDepth][4];
-    auto fetch = [&](int slot, int chunk) {
-      const uint4* src = base + (size_t)chunk * (2 * kChunkBytes / 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r[slot][j] = __ldg(src + j);
-    };
-    // chunks_per_tile is even, so the within-tile index of chunk g has the parity of g
-    int fidx = cpar;
-    int64_t gf = cpar;
-#pragma unroll
-    for (int i = 0; i < kDepth; ++i) {
-      if (gf < total_chunks) {
-        fetch(i, fidx);
-        fidx += kLoadPerQuarter;
-        if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
-        gf += kLoadPerQuarter;
+  if (warp == kTmaWarp) {
+    // ===================== TMA producer: this CTA's chunks, L2 -> shared-memory staging ring =========
+    if (lane == 0) {
+      const unsigned char* src = P.w + (size_t)rank * kWChunkBytes;
+      int idx = 0;  // chunk within the tile
+      for (int64_t c = 0; c < total_chunks; ++c) {
+        const int s = (int)(c % kSStages);
+        if (c >= kSStages) mbar_wait(&sc->s_empty[s], (uint32_t)((c / kSStages - 1) & 1));
+        mbar_expect_tx(&sc->s_full[s], kWChunkBytes);
+        tma_bulk_g2s(smem_u32(smem + kOffStage + s * kWChunkBytes), src + (size_t)idx * (2 * kWChunkBytes), kWChunkBytes,
+                     &sc->s_full[s]);
+        if (++idx == P.chunks_per_tile) idx = 0;
       }
     }
-    const uint32_t full0 = mapa_u32(smem_u32(&sc->a_full[0]), 0);  // the leader's barriers
-    int stage = cpar;
-    uint32_t par = 0;
-    bool first_pass = true;
-    int64_t g = cpar;
-    while (g < total_chunks) {
-#pragma unroll
-      for (int i = 0; i < kDepth; ++i) {
-        if (g < total_chunks) {
-          if (!first_pass) mbar_wait(&sc->a_empty[stage], par);
+  } else if (warp == kCpWarp) {
+    if (lane == 0) {
+      if (rank != 0) {
+        // ===================== peer: tell the leader when a chunk has landed here ==================
+        const uint32_t pf0 = mapa_u32(smem_u32(&sc->peer_full[0]), 0);
+        for (int64_t c = 0; c < total_chunks; ++c) {
+          const int s = (int)(c % kSStages);
+          mbar_wait(&sc->s_full[s], (uint32_t)((c / kSStages) & 1));
+          mbar_arrive_cluster_relaxed(pf0 + 8 * s);  // the data stays in this CTA; its tcgen05.cp is ordered by the TMA completion observed here
+        }
+      } else {
+        // ===================== leader: staged chunks of both CTAs -> tensor-memory ring ============
+        const uint32_t st0 = smem_u32(smem + kOffStage);
+        for (int64_t c = 0; c < total_chunks; ++c) {
+          const int s = (int)(c % kSStages), t = (int)(c % kARing);
+          const uint32_t ph = (uint32_t)((c / kSStages) & 1);
+          mbar_wait(&sc->s_full[s], ph);
+          mbar_wait(&sc->peer_full[s], ph);
+          if (c >= kARing) mbar_wait(&sc->a_empty[t], (uint32_t)((c / kARing - 1) & 1));
           tc_fence_after();
-          const uint32_t ta = tmem + lane_addr + kACol + stage * 16;
-          const uint32_t w0[8] = {r[i][0].x, r[i][0].y, r[i][0].z, r[i][0].w, r[i][1].x, r[i][1].y, r[i][1].z, r[i][1].w};
-          const uint32_t w1[8] = {r[i][2].x, r[i][2].y, r[i][2].z, r[i][2].w, r[i][3].x, r[i][3].y, r[i][3].z, r[i][3].w};
-          tmem_st16(ta, w0, w1);
-          if (gf < total_chunks) {
-            fetch(i, fidx);
-            fidx += kLoadPerQuarter;
-            if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
-            gf += kLoadPerQuarter;
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
-          g += kLoadPerQuarter;
-          stage += kLoadPerQuarter;
-          if (stage >= kARing) {
-            stage -= kARing;
-            if (first_pass) first_pass = false;
-            else par ^= 1;
-          }
+          const uint32_t ta = tmem + kACol + t * (16 * kChunkK);
+          // per K-step: 4 KB hi -> columns +0..7, 4 KB lo -> columns +8..15 (K-major core matrices: LBO 128, SBO 256)
+#pragma unroll
+          for (int u = 0; u < 2 * kChunkK; ++u)
+            tmem_cp2_128x256b(ta + 8 * u, make_desc(st0 + s * kWChunkBytes + u * 4096, 128, 256));
+          mma2_commit(smem_u32(&sc->a_full[t]), 1);   // MMA warp: the chunk is in tensor memory (both CTAs)
+          mma2_commit(smem_u32(&sc->s_empty[s]), 3);  // producers of both CTAs: the staging slot is free
         }
       }
     }
@@ -396,13 +441,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
         for (int si = 0; si < P.n_steps; ++si) {
           const Step& st = P.step[si];
           const int tl = (int)(t * P.n_steps + si);
-          const bool stamp = P.timeline && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
+          const bool stamp = P.timeline && !(P.debug & 128) && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
           const bool value_only = P.eval && st.colour;
           const uint32_t idesc = value_only ? make_idesc(256, 2 * 16, 0, 1) : make_idesc(256, 2 * 64, 0, 1);
-          const int nA = st.aux_ksteps, nH = st.h_ksteps, nT = nA + nH;
-          // K-step ks of the chunk stream reads AUX or H: [0, nA) AUX then H when aux_first, else H then AUX
+          // in chunks of kChunkK K-steps (AUX and H extents are multiples of it)
+          const int nA = st.aux_ksteps / kChunkK, nH = st.h_ksteps / kChunkK, nT = nA + nH;
+          // chunk i of the stream reads AUX or H: [0, nA) AUX then H when aux_first, else H then AUX
           const int first_n = st.aux_first ? nA : nH;
-          // two-pass groups of at most NEDDF_TC2_GROUP K-steps (the ring holds a whole group)
+          // two-pass groups of at most NEDDF_TC2_GROUP chunks (the ring holds a whole group)
           const int n_groups = (nT + NEDDF_TC2_GROUP - 1) / NEDDF_TC2_GROUP;
           const int g_len = (nT + n_groups - 1) / n_groups;
           bool norm_waited = !(st.colour && st.aux_ksteps > 0);  // colour layer 0 reads the normals from AUX
@@ -437,21 +483,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
                       mbar_wait(&sc->a_full[stage], full_par);
                       tc_fence_after();
                     }
-                    const uint32_t ta = tmem + kACol + stage * 16;
-                    mma2_f16_ts_elect(d, ta, db_hi, idesc, acc);
-                    mma2_f16_ts_elect(d, ta + 8, db_hi, idesc, 1);
-                    mma2_f16_ts_elect(d, ta, db_lo, idesc, 1);
-                    if (hs == 1) mma2_commit_elect(smem_u32(&sc->a_empty[stage]), 3);
+                    const uint32_t ta = tmem + kACol + stage * (16 * kChunkK);
+#pragma unroll
+                    for (int u = 0; u < kChunkK; ++u) {
+                      mma2_f16_ts_elect(d, ta + 16 * u, db_hi + 16 * u, idesc, u ? 1u : acc);
+                      mma2_f16_ts_elect(d, ta + 16 * u + 8, db_hi + 16 * u, idesc, 1);
+                      mma2_f16_ts_elect(d, ta + 16 * u, db_lo + 16 * u, idesc, 1);
+                    }
+                    if (hs == 1) mma2_commit_elect(smem_u32(&sc->a_empty[stage]), 1);
                   } else if (hs == 0) {
-                    mbar_wait(&sc->a_full[stage], full_par);
+                    if (!(P.debug & 4)) mbar_wait(&sc->a_full[stage], full_par);
                     tc_fence_after();
-                    chunk_mma2_elect<false>(d, tmem + kACol + stage * 16, db_hi, db_lo, idesc, acc, 0);
+                    if (!(P.debug & 64)) chunk_mma2_elect<false>(d, tmem + kACol + stage * (16 * kChunkK), db_hi, db_lo, idesc, acc, 0);
+                  } else if (P.debug & 64) {
+                    mma2_commit_elect(smem_u32(&sc->a_empty[stage]), 1);
                   } else {
-                    chunk_mma2_elect<true>(d, tmem + kACol + stage * 16, db_hi, db_lo, idesc, acc, smem_u32(&sc->a_empty[stage]));
+                    chunk_mma2_elect<true>(d, tmem + kACol + stage * (16 * kChunkK), db_hi, db_lo, idesc, acc, smem_u32(&sc->a_empty[stage]));
                   }
                   acc = 1;
-                  db_hi += 16;  // 16 K = 256 bytes in descriptor units
-                  db_lo += 16;
+                  db_hi += 16 * kChunkK;  // 16 K = 256 bytes = 16 descriptor units per K-step
+                  db_lo += 16 * kChunkK;
                   if (++stage == kARing) {
                     stage = 0;
                     full_par ^= 1;
@@ -464,9 +515,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               const bool part1_aux = st.aux_first != 0;
               if (b1 < e1) {
                 if (part1_aux) {
-                  run(dba_hi + b1 * 16, dba_lo + b1 * 16, e1 - b1);
+                  run(dba_hi + b1 * (16 * kChunkK), dba_lo + b1 * (16 * kChunkK), e1 - b1);
                 } else {
-                  run(dbh_hi + b1 * 16, dbh_lo + b1 * 16, e1 - b1);
+                  run(dbh_hi + b1 * (16 * kChunkK), dbh_lo + b1 * (16 * kChunkK), e1 - b1);
                 }
               }
               if (b2 < e2) {
@@ -477,9 +528,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
                     norm_phase ^= 1;
                     norm_waited = true;
                   }
-                  run(dba_hi + (b2 - first_n) * 16, dba_lo + (b2 - first_n) * 16, e2 - b2);
+                  run(dba_hi + (b2 - first_n) * (16 * kChunkK), dba_lo + (b2 - first_n) * (16 * kChunkK), e2 - b2);
                 } else {
-                  run(dbh_hi + (b2 - first_n) * 16, dbh_lo + (b2 - first_n) * 16, e2 - b2);
+                  run(dbh_hi + (b2 - first_n) * (16 * kChunkK), dbh_lo + (b2 - first_n) * (16 * kChunkK), e2 - b2);
                 }
               }
               if (ge == nT) mma2_commit_elect(smem_u32(&sc->acc_ready[hs]), 3);
@@ -500,9 +551,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
     const int ch = 128 * (int)rank + chl;    // output channel = K index of the next layer
     const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
     const bool remote = tcta != rank;
+    const bool skip_remote = remote && (P.debug & 32);
     // destination operand buffers: own shared memory or the peer's
     const uint32_t dst_hhi = mapa_u32(smem_u32(h_hi), tcta), dst_hlo = mapa_u32(smem_u32(h_lo), tcta);
-    const uint32_t dst_hsum = mapa_u32(smem_u32(&sc->hsum[4 * rank + quarter][0][0][0]), tcta);
+    const uint32_t dst_hsum = mapa_u32(smem_u32(&sc->hsum[4 * rank + quarter][0][0]), tcta);
     const uint32_t act0 = mapa_u32(smem_u32(&sc->act_ready[0]), 0);
     const uint32_t norm0 = mapa_u32(smem_u32(&sc->norm_ready), 0);
     __half2 bad = __floats2half2_rn(0.f, 0.f);  // max |operand hi part| seen (fp16 range check)
@@ -549,9 +601,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
       fence_async_all();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kEpiThreads) : "memory");
       if (tid == 0) {
-        if (cbar0) mbar_arrive_cluster(cbar0);
-        if (cbar1) mbar_arrive_cluster(cbar1);
-        if (cbar2) mbar_arrive_cluster(cbar2);
+        fence_acq_rel_cluster();  // one release for the (up to) three signals
+        if (cbar0) mbar_arrive_cluster_relaxed(cbar0);
+        if (cbar1) mbar_arrive_cluster_relaxed(cbar1);
+        if (cbar2) mbar_arrive_cluster_relaxed(cbar2);
       }
     };
     const uint32_t head_ready_c0 = mapa_u32(smem_u32(&sc->head_ready[0]), 0), head_ready_c1 = mapa_u32(smem_u32(&sc->head_ready[0]), 1);
@@ -570,7 +623,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
         const bool value_only = P.eval && st.colour;
         const bool last = (t + 1 == my_tiles) && (si + 1 == P.n_steps);
         const int tl = (int)(t * P.n_steps + si);
-        const bool stamp = P.timeline && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
+        const bool stamp = P.timeline && !(P.debug & 128) && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
         for (int hs = 0; hs < 2; ++hs) {
           if (lane == 0) mbar_wait(&sc->acc_ready[hs], acc_phase);
           __syncwarp();
@@ -590,6 +643,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               }
             }
           }
+          if (!(P.debug & 16)) {
           // this thread: channel ch, samples (CTA tcta, 16 hs + 8 sg + i), i = 0..7
           const uint32_t tbase = tmem + lane_addr + 128 * hs + (value_only ? 16 * tcta + 8 * sg : 64 * tcta + 8 * sg);
           const int s0 = 16 * hs + 8 * sg;                                         // local sample of i = 0
@@ -611,7 +665,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
           if (write_h) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) split2h(x[2 * i], x[2 * i + 1], h[i], l[i], bad);
-            if (remote) {
+            if (skip_remote) {
+            } else if (remote) {
               st_cluster_v4(dst_hhi + off, make_uint4(h[0], h[1], h[2], h[3]));
               st_cluster_v4(dst_hlo + off, make_uint4(l[0], l[1], l[2], l[3]));
             } else {
@@ -631,7 +686,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               }
               warp_transpose_reduce16(hv, lane);  // lane L: sample L >> 2, output (L >> 1) & 1
               if ((lane & 1) == 0)
-                st_cluster_f32(dst_hsum + (uint32_t)((((s0 + (lane >> 2)) * 4 + j) * 4 + ((lane >> 1) & 1)) * 4), hv[0]);
+                st_cluster_f32(dst_hsum + (uint32_t)(((s0 + (lane >> 2)) * 12 + 3 * j + ((lane >> 1) & 1)) * 4), hv[0]);
             } else if (st.head == 2) {
               float hv[32];
 #pragma unroll
@@ -642,7 +697,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
                 hv[4 * i + 3] = 0.f;
               }
               warp_transpose_reduce<32>(hv, lane);  // lane L: sample L >> 2, output L & 3
-              st_cluster_f32(dst_hsum + (uint32_t)((((s0 + (lane >> 2)) * 4 + j) * 4 + (lane & 3)) * 4), hv[0]);
+              if ((lane & 3) != 3) st_cluster_f32(dst_hsum + (uint32_t)(((s0 + (lane >> 2)) * 12 + 3 * j + (lane & 3)) * 4), hv[0]);
             }
           };
           head_rows(x, 0);
@@ -662,7 +717,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
 #pragma unroll
                 for (int i = 0; i < 4; ++i) split2h(g[2 * i], g[2 * i + 1], h[i], l[i], bad);
                 off += 2 * (kHK * 16);
-                if (remote) {
+                if (skip_remote) {
+                } else if (remote) {
                   st_cluster_v4(dst_hhi + off, make_uint4(h[0], h[1], h[2], h[3]));
                   st_cluster_v4(dst_hlo + off, make_uint4(l[0], l[1], l[2], l[3]));
                 } else {
@@ -673,6 +729,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               head_rows(g, j);
             }
           }
+          }  // debug & 16
           tc_fence_before();
           if (stamp) P.timeline[6 * tl + 3 + 2 * hs] = clock64();
           // accumulator hs drained, operand rows of half hs rewritten in both CTAs, head sums parked
@@ -696,8 +753,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
             for (int c = 0; c < 8; ++c) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                ddf[j] += sc->hsum[c][s][j][0];
-                aux[j] += sc->hsum[c][s][j][1];
+                ddf[j] += sc->hsum[c][s][3 * j + 0];
+                aux[j] += sc->hsum[c][s][3 * j + 1];
               }
             }
             ddf[0] += __ldg(p.b_head + 0);
@@ -719,10 +776,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
             for (int c = 0; c < 8; ++c) {
 #pragma unroll
               for (int o = 0; o < 3; ++o) {
-                col[o] += sc->hsum[c][s][0][o];
+                col[o] += sc->hsum[c][s][o];
                 if (!P.eval) {
 #pragma unroll
-                  for (int i = 0; i < 3; ++i) colJ[i][o] += sc->hsum[c][s][1 + i][o];
+                  for (int i = 0; i < 3; ++i) colJ[i][o] += sc->hsum[c][s][3 * (1 + i) + o];
                 }
               }
             }
@@ -767,7 +824,7 @@ struct PackArgs {
   int aux_pad[kMaxHidden];    // their padded K extent in AUX
   int aux_first[kMaxHidden];  // AUX K-steps first (1) or after the H K-steps (0)
   int ksteps[kMaxHidden];
-  int chunk0[kMaxHidden];     // first per-CTA chunk index of the layer
+  int chunk0[kMaxHidden];     // first per-CTA chunk index (chunks of kChunkK K-steps) of the layer
   int n_hidden;
 };
 
@@ -787,10 +844,11 @@ __global__ void pack_hidden_kernel(PackArgs a, unsigned char* __restrict__ dst, 
     float w = (row >= 0) ? a.w[l][(size_t)row * kWidth + 128 * rank + m] : 0.f;
     __half hi = __float2half_rn(w);
     __half lo = __float2half_rn(w - __half2float(hi));
-    unsigned char* chunk = dst + ((size_t)(a.chunk0[l] + ks) * 2 + rank) * kChunkBytes;
-    // tensor-memory A layout: row m = lane, k pairs packed per 32-bit column; 8 hi words then 8 lo words
-    *reinterpret_cast<__half*>(chunk + m * 64 + k * 2) = hi;
-    *reinterpret_cast<__half*>(chunk + m * 64 + 32 + k * 2) = lo;
+    // chunk = kChunkK K-steps of this rank; per K-step 4 KB hi then 4 KB lo, each a K-major core-matrix block
+    // [m/8][k/8][m%8][k%8] (what tcgen05.cp.128x256b moves to lane m, columns k/2)
+    unsigned char* chunk = dst + ((size_t)(a.chunk0[l] + ks / kChunkK) * 2 + rank) * kWChunkBytes + (size_t)(ks % kChunkK) * kChunkBytes;
+    *reinterpret_cast<__half*>(chunk + wchunk_off(m, k)) = hi;
+    *reinterpret_cast<__half*>(chunk + 4096 + wchunk_off(m, k)) = lo;
   }
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < kWidth; c += blockDim.x) bias[l * kWidth + c] = a.b[l][c];
@@ -871,7 +929,7 @@ static int32_t tc2_ensure(neddf_field* f) {
     S->pack.aux_first[l] = aux_first;
     S->pack.ksteps[l] = st.aux_ksteps + st.h_ksteps;
     S->pack.chunk0[l] = chunk;
-    chunk += S->pack.ksteps[l];
+    chunk += S->pack.ksteps[l] / tc2::kChunkK;  // AUX (64 / 96 K) and H (256 K) extents are multiples of 32 K
   }
   S->n_steps = n_hidden;
   S->chunks_per_tile = chunk;
@@ -880,7 +938,7 @@ static int32_t tc2_ensure(neddf_field* f) {
   // AUX is dead again: the next tile's prologue goes there.
   S->step[last_aux].post = 1;
   S->step[f->n_ddf].post = 2;
-  if (cudaMalloc(&S->d_w, (size_t)chunk * 2 * tc::kChunkBytes) != cudaSuccess ||
+  if (cudaMalloc(&S->d_w, (size_t)chunk * 2 * tc2::kWChunkBytes) != cudaSuccess ||
       cudaMalloc(&S->d_bias, (size_t)n_hidden * kWidth * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&S->d_w_head, (size_t)kWidth * 8 * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess) {

@@ -156,10 +156,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
   if (tid == 0 && reinterpret_cast<volatile uint32_t*>(smem)[3] == 0xdeadbeefu) out[blockIdx.x] = -1;
 }
 
+// tcgen05.cp layout probe: shared memory holds the 16-bit pattern value[i] = i (i = half index); one
+// 128x256b copy with the given descriptor strides lands in tensor-memory columns 0..7; out[lane][col] =
+// the 32-bit column value (two half indices), so the host can read off which bytes went where.
+__global__ void __launch_bounds__(128, 1) tc_cp_probe_kernel(int lbo, int sbo, uint32_t* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16384; i += 128) reinterpret_cast<uint16_t*>(smem)[i] = (uint16_t)i;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 32);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint64_t desc = make_desc(smem_u32(smem), (uint32_t)lbo, (uint32_t)sbo);
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem), "l"(desc) : "memory");
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  float v[8];
+  tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16), v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[tid * 8 + i] = __float_as_uint(v[i]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
 }  // namespace tc
 }  // namespace neddf
 
 using namespace neddf;
+
+extern "C" int32_t neddf_tc_cp_probe(int32_t lbo, int32_t sbo, uint32_t* d_out, void* stream) {
+  if (!d_out || lbo < 0 || sbo < 0 || (lbo % 16) || (sbo % 16)) return fail(NEDDF_E_INVALID, "neddf_tc_cp_probe: bad arguments");
+  NEDDF_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_cp_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+  tc::tc_cp_probe_kernel<<<1, 128, 32768, (cudaStream_t)stream>>>(lbo, sbo, d_out);
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}
+
 
 extern "C" int32_t neddf_tc_pair_selftest(const float* d_a, const float* d_b, int32_t n, int32_t k, float* d_c,
                                           int64_t* d_cycles, int32_t reps, void* stream) {

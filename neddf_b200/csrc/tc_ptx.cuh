@@ -315,6 +315,12 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t caddr, float v) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
+// arrive without any memory fence (the data handed over is tensor memory, ordered by tcgen05 fences, or
+// was already published by an explicit fence)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // wait with acquire at cluster scope (the barrier is local; the arrivals may come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
