@@ -49,7 +49,7 @@ extern "C" {
 #define NEDDF_UV_F32 3
 
 /* field engines */
-#define NEDDF_ENGINE_AUTO 0  /* TC2 when the configuration allows, else TC, else fp32 */
+#define NEDDF_ENGINE_AUTO 0  /* TC when the configuration allows, else TC2, else fp32 */
 #define NEDDF_ENGINE_FP32 1  /* CUDA-core fp32 FMA megakernel (bit-faithful fp32 arithmetic) */
 #define NEDDF_ENGINE_TC 2    /* tcgen05 megakernel, 3-product fp16-split operands, fp32 accumulate; one CTA per SM */
 #define NEDDF_ENGINE_TC2 3   /* same arithmetic, CTA pairs (tcgen05 cta_group::2): half the weight stream per sample */

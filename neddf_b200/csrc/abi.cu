@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstring>
 #include <atomic>
+#include <cstdlib>
 #include <new>
 
 #include "field.cuh"
@@ -225,11 +226,17 @@ extern "C" int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_fie
   return NEDDF_OK;
 }
 
-// AUTO: the CTA-pair tensor-core kernel when the configuration fits it, else the single-CTA one,
-// else fp32 FMA
+// AUTO: the single-CTA tensor-core kernel where it applies (the faster of the two today:
+// profiles/r02_summary.md), else the CTA-pair kernel (wider configuration coverage: any embedding ranks
+// that fit the 64 / 96 K of AUX), else fp32 FMA.  NEDDF_AUTO_ENGINE=tc2 flips the preference.
 static int32_t auto_engine(const neddf_field* f) {
-  if (tc2_supported(f)) return NEDDF_ENGINE_TC2;
+  static const bool prefer_pair = [] {
+    const char* e = std::getenv("NEDDF_AUTO_ENGINE");
+    return e && std::string(e) == "tc2";
+  }();
+  if (prefer_pair && tc2_supported(f)) return NEDDF_ENGINE_TC2;
   if (tc_supported(f)) return NEDDF_ENGINE_TC;
+  if (tc2_supported(f)) return NEDDF_ENGINE_TC2;
   return NEDDF_ENGINE_FP32;
 }
 

@@ -62,6 +62,10 @@ constexpr int kPairS = 2 * kTileS;  // samples per pair tile
 constexpr int kChunkK = 2;                            // K-steps per weight chunk
 constexpr int kWChunkBytes = kChunkK * kChunkBytes;   // 16 KB per CTA and chunk
 constexpr int kARing = 8;                             // chunks resident in tensor memory (32 columns each)
+#ifndef NEDDF_TC2_TMA_SPLIT
+#define NEDDF_TC2_TMA_SPLIT 1
+#endif
+constexpr int kTmaSplit = NEDDF_TC2_TMA_SPLIT;          // bulk copies per chunk
 constexpr int kSStages = 2;                           // shared-memory staging ring of the TMA copies
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -97,6 +101,7 @@ struct Scratch {
   uint64_t acc_ready[2];     // MMA -> epilogue warps (multicast commit): accumulator hs complete
   uint64_t head_ready[2];    // partial head sums of this CTA's samples of half hs are in hsum
   uint64_t norm_ready;       // (leader) both CTAs wrote the surface normals into AUX
+  long long t_issue[kSStages];  // profiling aid: when the producer issued the copy into each staging slot
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -130,6 +135,7 @@ struct Tc2Params {
                         // 2 = delay the first MMA of every step, 4 = MMA warp does not wait for weight chunks, 8 = loaders skip
                         // the L2 reads, 16 = epilogue skips its math and stores, 32 = no remote stores (peer rows stay stale),
                         // 64 = no MMAs
+  int group;            // chunks per two-pass group (1..kARing)
   int col8;             // == 8: TMEM column offsets are formed at run time (see tmem column note in the epilogue)
   float* dump;          // debugging aid: cluster 0 dumps AUX (hi) and the accumulators of (tile 0, step dump_step)
   int dump_step;
@@ -393,9 +399,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
       for (int64_t c = 0; c < total_chunks; ++c) {
         const int s = (int)(c % kSStages);
         if (c >= kSStages) mbar_wait(&sc->s_empty[s], (uint32_t)((c / kSStages - 1) & 1));
+        if (P.debug & 128) sc->t_issue[s] = clock64();
         mbar_expect_tx(&sc->s_full[s], kWChunkBytes);
-        tma_bulk_g2s(smem_u32(smem + kOffStage + s * kWChunkBytes), src + (size_t)idx * (2 * kWChunkBytes), kWChunkBytes,
-                     &sc->s_full[s]);
+        // several smaller copies on one barrier: their L2 round trips overlap (one 16 KB request is served serially)
+#pragma unroll
+        for (int u = 0; u < kTmaSplit; ++u)
+          tma_bulk_g2s(smem_u32(smem + kOffStage + s * kWChunkBytes + u * (kWChunkBytes / kTmaSplit)),
+                       src + (size_t)idx * (2 * kWChunkBytes) + u * (kWChunkBytes / kTmaSplit), kWChunkBytes / kTmaSplit,
+                       &sc->s_full[s]);
         if (++idx == P.chunks_per_tile) idx = 0;
       }
     }
@@ -415,10 +426,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
         for (int64_t c = 0; c < total_chunks; ++c) {
           const int s = (int)(c % kSStages), t = (int)(c % kARing);
           const uint32_t ph = (uint32_t)((c / kSStages) & 1);
+          const bool cstamp = P.timeline && (P.debug & 128) && blockIdx.x == 0 && (c + 1) * 6 <= P.timeline_cap;
+          const long long ct0 = cstamp ? clock64() : 0;
           mbar_wait(&sc->s_full[s], ph);
+          const long long ct1 = cstamp ? clock64() : 0;
+          const long long ti = cstamp ? sc->t_issue[s] : 0;
           mbar_wait(&sc->peer_full[s], ph);
+          const long long ct2 = cstamp ? clock64() : 0;
           if (c >= kARing) mbar_wait(&sc->a_empty[t], (uint32_t)((c / kARing - 1) & 1));
           tc_fence_after();
+          if (cstamp) {
+            P.timeline[6 * c + 0] = ct0;          // start waiting for this chunk
+            P.timeline[6 * c + 1] = ti;           // producer issued its TMA
+            P.timeline[6 * c + 2] = ct1;          // landed here
+            P.timeline[6 * c + 3] = ct2;          // peer's landed
+            P.timeline[6 * c + 4] = clock64();    // tensor-memory stage free
+          }
           const uint32_t ta = tmem + kACol + t * (16 * kChunkK);
           // per K-step: 4 KB hi -> columns +0..7, 4 KB lo -> columns +8..15 (K-major core matrices: LBO 128, SBO 256)
 #pragma unroll
@@ -437,11 +460,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
       uint32_t full_par = 0;  // parity to wait for on a_full[stage]
       uint32_t act_phase = 0;
       uint32_t norm_phase = 0;
+      int mst = 0;  // profiling stamps of the MMA warp (NEDDF_TC2_DEBUG & 512)
       for (int64_t t = 0; t < my_tiles; ++t) {
         for (int si = 0; si < P.n_steps; ++si) {
           const Step& st = P.step[si];
           const int tl = (int)(t * P.n_steps + si);
-          const bool stamp = P.timeline && !(P.debug & 128) && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
+          const bool stamp = P.timeline && !(P.debug & (128 | 512)) && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
           const bool value_only = P.eval && st.colour;
           const uint32_t idesc = value_only ? make_idesc(256, 2 * 16, 0, 1) : make_idesc(256, 2 * 64, 0, 1);
           // in chunks of kChunkK K-steps (AUX and H extents are multiples of it)
@@ -449,7 +473,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
           // chunk i of the stream reads AUX or H: [0, nA) AUX then H when aux_first, else H then AUX
           const int first_n = st.aux_first ? nA : nH;
           // two-pass groups of at most NEDDF_TC2_GROUP chunks (the ring holds a whole group)
-          const int n_groups = (nT + NEDDF_TC2_GROUP - 1) / NEDDF_TC2_GROUP;
+          const int n_groups = (nT + P.group - 1) / P.group;
           const int g_len = (nT + n_groups - 1) / n_groups;
           bool norm_waited = !(st.colour && st.aux_ksteps > 0);  // colour layer 0 reads the normals from AUX
           if (stamp) P.timeline[6 * tl + 0] = clock64();
@@ -478,6 +502,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               }
               auto run = [&](uint64_t db_hi, uint64_t db_lo, int n) {
                 for (int i = 0; i < n; ++i) {
+                  const bool mstamp = P.timeline && (P.debug & 512) && blockIdx.x == 0 && lane == 0 && t == 1 && (mst + 1) * 4 <= P.timeline_cap;
+                  const long long mt0 = mstamp ? clock64() : 0;
                   if (P.debug & 1) {
                     if (hs == 0) {
                       mbar_wait(&sc->a_full[stage], full_par);
@@ -499,6 +525,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
                     mma2_commit_elect(smem_u32(&sc->a_empty[stage]), 1);
                   } else {
                     chunk_mma2_elect<true>(d, tmem + kACol + stage * (16 * kChunkK), db_hi, db_lo, idesc, acc, smem_u32(&sc->a_empty[stage]));
+                  }
+                  if (mstamp) {
+                    P.timeline[4 * mst + 0] = mt0;
+                    P.timeline[4 * mst + 1] = clock64();
+                    P.timeline[4 * mst + 2] = si * 16 + hs * 8 + stage;
+                    ++mst;
                   }
                   acc = 1;
                   db_hi += 16 * kChunkK;  // 16 K = 256 bytes = 16 descriptor units per K-step
@@ -601,10 +633,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
       fence_async_all();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kEpiThreads) : "memory");
       if (tid == 0) {
-        fence_acq_rel_cluster();  // one release for the (up to) three signals
-        if (cbar0) mbar_arrive_cluster_relaxed(cbar0);
-        if (cbar1) mbar_arrive_cluster_relaxed(cbar1);
-        if (cbar2) mbar_arrive_cluster_relaxed(cbar2);
+        if (P.debug & 256) {  // experiment: CTA-scope release only (no MEMBAR.ALL.GPU)
+          if (cbar0) mbar_arrive_cluster_default(cbar0);
+          if (cbar1) mbar_arrive_cluster_default(cbar1);
+          if (cbar2) mbar_arrive_cluster_default(cbar2);
+        } else {
+          fence_acq_rel_cluster();  // one release for the (up to) three signals
+          if (cbar0) mbar_arrive_cluster_relaxed(cbar0);
+          if (cbar1) mbar_arrive_cluster_relaxed(cbar1);
+          if (cbar2) mbar_arrive_cluster_relaxed(cbar2);
+        }
       }
     };
     const uint32_t head_ready_c0 = mapa_u32(smem_u32(&sc->head_ready[0]), 0), head_ready_c1 = mapa_u32(smem_u32(&sc->head_ready[0]), 1);
@@ -623,7 +661,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
         const bool value_only = P.eval && st.colour;
         const bool last = (t + 1 == my_tiles) && (si + 1 == P.n_steps);
         const int tl = (int)(t * P.n_steps + si);
-        const bool stamp = P.timeline && !(P.debug & 128) && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
+        const bool stamp = P.timeline && !(P.debug & (128 | 512)) && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
         for (int hs = 0; hs < 2; ++hs) {
           if (lane == 0) mbar_wait(&sc->acc_ready[hs], acc_phase);
           __syncwarp();
@@ -648,8 +686,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
           const uint32_t tbase = tmem + lane_addr + 128 * hs + (value_only ? 16 * tcta + 8 * sg : 64 * tcta + 8 * sg);
           const int s0 = 16 * hs + 8 * sg;                                         // local sample of i = 0
           const int64_t ng0 = tile * kPairS + kTileS * (int64_t)tcta + s0;         // its global index
-          float x[8], d1[8];
-          tmem_ld8(tbase, x);
+          float x[8], d1[8], gj[3][8];
+          if (value_only) tmem_ld8(tbase, x);
+          else tmem_ld8x4(tbase, tbase + 2 * P.col8, tbase + 4 * P.col8, tbase + 6 * P.col8, x, gj[0], gj[1], gj[2]);  // one wait for the four row types
           float* save = nullptr;  // training: pre-activations [layer][sample][row type][channel]
           if (p.save_pre) save = p.save_pre + (((size_t)st.bias_off / kWidth * p.n + ng0) * 4) * kWidth + ch;
           if (save) {
@@ -704,8 +743,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
           if (!value_only) {
 #pragma unroll
             for (int j = 1; j < 4; ++j) {  // Jacobian rows: G = f'(x) J (tanh_exp.py:47-48)
-              float g[8];
-              tmem_ld8(tbase + 2 * P.col8 * j, g);
+              float (&g)[8] = gj[j - 1];
               if (save) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -995,6 +1033,8 @@ int32_t launch_field_tc2(const neddf_field* f, FieldParams& p, int flags, cudaSt
   P.timeline = S->timeline;
   P.timeline_cap = S->timeline_cap;
   P.col8 = 8;
+  P.group = NEDDF_TC2_GROUP;
+  if (const char* e = std::getenv("NEDDF_TC2_GROUP")) P.group = std::max(1, std::min(tc2::kARing, std::atoi(e)));
   P.debug = 0;
   if (const char* e = std::getenv("NEDDF_TC2_DEBUG")) P.debug = std::atoi(e);
   P.dump = S->dump;

@@ -320,6 +320,33 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t caddr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
+// default semantics (release at CTA scope): what CUTLASS's ClusterBarrier::arrive(cta_id) uses for DSMEM hand-offs
+__device__ __forceinline__ void mbar_arrive_cluster_default(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+// four 8-column loads in flight, one wait (lane = TMEM lane, 4 x 8 consecutive columns at taddr + stride * j)
+__device__ __forceinline__ void tmem_ld8x4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, float a[8], float b[8], float c[8], float d[8]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%33];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%34];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%24,%25,%26,%27,%28,%29,%30,%31}, [%35];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(t0), "r"(t1), "r"(t2), "r"(t3)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(r[8 + i]);
+    c[i] = __uint_as_float(r[16 + i]);
+    d[i] = __uint_as_float(r[24 + i]);
+  }
+}
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // wait with acquire at cluster scope (the barrier is local; the arrivals may come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {

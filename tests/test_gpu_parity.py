@@ -490,14 +490,15 @@ def test_composite_backward_matches_autograd(name):
     assert float(dd.grad[:, -1].abs().max()) == 0.0  # the closing edge receives no gradient
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", ["train", "bunny"])
-def test_field_backward_matches_autograd(name):
-    """Training path of the field (neddf_field_forward_train + neddf_field_backward + cuBLAS weight
-    gradients) against autograd through the oracle, for random upstream gradients of density,
+def test_field_backward_matches_autograd(name, engine):
+    """Training path of the field (neddf_field_forward_train of the module's engine + neddf_field_backward +
+    weight gradients) against autograd through the oracle, for random upstream gradients of density,
     colour and fields_penalty."""
     G = _gpu()
     c = Case(name)
-    render = G.build_render(c, "fp32")
+    render = G.build_render(c, engine)
     net = render.network_fine
     n_rays = 6
     d, o = orc.make_rays(c.t("uv")[:n_rays], c.cam)
@@ -590,3 +591,32 @@ def test_network_forward_sampling_is_differentiable():
         for part in mod.split("."):
             obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
         assert nerr(getattr(obj, attr).grad.cpu().numpy(), Pg[k].grad.numpy()) < 2e-3, k
+
+
+def test_other_embedding_ranks_run_on_a_tensor_core_engine():
+    """The reference's own test fixture uses embed_pos_rank=6 (tests/conftest.py:77-99); the single-CTA
+    tensor-core kernel is built for ranks 10/4 only, the CTA-pair kernel covers any ranks that fit AUX:
+    "auto" must not fall to the 9x slower fp32 engine, and the result must match the oracle."""
+    G = _gpu()
+    import neddf_b200
+    cfg = dict(embed_pos_rank=6, embed_dir_rank=2, ddf_layer_count=5, col_layer_count=3, skips=[1],
+               activation_type="tanhExp", density_activation_type="LeakyReLU", d_near=0.01, lowpass_alpha_offset=6.0)
+    fc = orc.FieldConfig(**cfg)
+    P = orc.init_params(fc, 5, bias_std=0.05)
+    net = neddf_b200.NeDDF(**cfg)
+    net.load_state_dict(P)
+    net.to(G.DEV)
+    net.set_iter(-1)
+    assert net.resolved_engine() == "tc2"
+    g = torch.Generator().manual_seed(3)
+    B, S = 5, 37
+    pos = (torch.rand(B, S, 3, generator=g) - 0.5) * 2.0
+    dd = torch.nn.functional.normalize(torch.randn(B, S, 3, generator=g), dim=-1)
+    var = torch.rand(B, S, 3, generator=g) * 1e-3
+    st = orc.FieldState.at_iter(fc, -1)
+    with torch.no_grad():
+        ref = orc.field_forward(P, fc, st, pos, dd, var)
+        out = net(neddf_b200.Sampling(pos.to(G.DEV), dd.to(G.DEV), var.to(G.DEV)))
+    for k in ("distance", "density", "color", "fields_penalty", "aux_grad"):
+        assert nerr(out[k].cpu().numpy(), ref[k].numpy()) < PARITY_TOL, k
+    net.check_engine_status()

@@ -14,7 +14,10 @@ render = neddf_b200.NeRFRender(network_config=bench.NET_CFG, **bench.RENDER_CFG)
 render.load_state_dict(sd); render.to(dev); render.set_iter(-1); render.set_engine("tc2"); render.check_nan = False
 n_rays = 65536
 render.render_pixels(bench.W, bench.H, cam, ["color", "depth"], 1, first, n_rays)
-for m in modes:
+groups = [int(g) for g in os.environ.get("TC2_GROUPS", "8").split(",")]
+for m in [(mm, g) for g in groups for mm in modes]:
+    os.environ["NEDDF_TC2_GROUP"] = str(m[1])
+    m = m[0]
     os.environ["NEDDF_TC2_DEBUG"] = str(m)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -23,4 +26,4 @@ for m in modes:
         render.render_pixels(bench.W, bench.H, cam, ["color", "depth"], 1, first, n_rays)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 2
-    print(f"debug {m:3d}: {n_rays * bench.EVALS_PER_RAY / ms * 1e3:.3e} evaluations/s", flush=True)
+    print(f"group {os.environ['NEDDF_TC2_GROUP']} debug {m:3d}: {n_rays * bench.EVALS_PER_RAY / ms * 1e3:.3e} evaluations/s", flush=True)
