@@ -119,6 +119,27 @@ int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* 
  * issue done, epilogue start, epilogue done.  Pass NULL to switch it off. */
 int32_t neddf_field_set_timeline(neddf_field_t* f, int64_t* d_buf, int32_t capacity);
 
+/* Early ray termination (BASELINE.json configs[4]; opt-in, not in the reference whose compositing visits every
+ * sample, base_neural_render.py:148-172).  The field on ONE depth segment: samples [edge0, edge0+seg_len) of the
+ * rays listed in d_ray_index[0 .. *d_n_active) (both NULL = all n_rays rays); density / colour are scattered to
+ * [ray, edge] of the full [n_rays, n_edges] arrays, which the caller zero-fills: a sample that is never
+ * evaluated has density 0 and contributes nothing to neddf_composite.  *d_n_active is read on the device. */
+int32_t neddf_field_forward_rays_segment(const neddf_field_t* f, const neddf_field_state_t* st,
+                                         const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
+                                         int64_t n_rays, int32_t n_edges, int32_t sampling_type, float ray_radius,
+                                         int32_t edge0, int32_t seg_len, const int32_t* d_ray_index,
+                                         const int32_t* d_n_active, float* d_density, float* d_color,
+                                         int32_t engine, void* stream);
+
+/* After a segment: d_transmittance[ray] *= prod_j (1 - o_j + 1e-7) over the segment's intervals (the factors of
+ * base_neural_render.py:148-160), and the rays with transmittance > eps are written to d_idx_out / *d_n_out
+ * (order without meaning).  d_executed (optional, uint64) accumulates rays_in * seg_len = MLP evaluations
+ * actually executed.  d_idx_in / d_n_in NULL = all rays. */
+int32_t neddf_terminate_rays(const float* d_dists, const float* d_density, int64_t n_rays, int32_t n_edges,
+                             int32_t edge0, int32_t seg_len, const int32_t* d_idx_in, const int32_t* d_n_in,
+                             float* d_transmittance, float eps, int32_t* d_idx_out, int32_t* d_n_out,
+                             uint64_t* d_executed, void* stream);
+
 /* Debugging aid for the tensor-core pair engine: when d_buf != NULL, cluster 0 of every following
  * launch copies, at (its first tile, hidden step `step`), per CTA the AUX operand buffer (hi parts,
  * 6144 words) and both accumulator halves (2 x 128 lanes x 128 columns fp32) into

@@ -406,8 +406,41 @@ extern "C" int32_t neddf_field_forward_rays(const neddf_field_t* f, const neddf_
   return dispatch(f, p, flags, engine, (cudaStream_t)stream);
 }
 
+// Early ray termination (BASELINE.json configs[4]; not in the reference, whose compositing always visits
+// every sample - base_neural_render.py:148-172): the field on ONE depth segment [edge0, edge0 + seg_len)
+// of the rays in d_ray_index[0 .. *d_n_active), outputs scattered into the full [n_rays, n_edges] arrays.
+extern "C" int32_t neddf_field_forward_rays_segment(const neddf_field_t* f, const neddf_field_state_t* st,
+                                                    const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
+                                                    int64_t n_rays, int32_t n_edges, int32_t sampling_type,
+                                                    float ray_radius, int32_t edge0, int32_t seg_len,
+                                                    const int32_t* d_ray_index, const int32_t* d_n_active,
+                                                    float* d_density, float* d_color, int32_t engine, void* stream) {
+  if (!f) return fail(NEDDF_E_INVALID, "neddf_field_forward_rays_segment: field is NULL");
+  if (!f->weights_set) return fail(NEDDF_E_INVALID, "neddf_field_forward_rays_segment: weights were never set");
+  if (n_rays < 0 || n_edges < 1 || edge0 < 0 || seg_len < 1 || edge0 + seg_len > n_edges)
+    return fail(NEDDF_E_INVALID, "neddf_field_forward_rays_segment: bad sizes");
+  if (sampling_type != NEDDF_SAMPLING_POINT && sampling_type != NEDDF_SAMPLING_CONE)
+    return fail(NEDDF_E_INVALID, "neddf_field_forward_rays_segment: unknown sampling type");
+  if (sampling_type == NEDDF_SAMPLING_CONE && n_edges < 2)
+    return fail(NEDDF_E_INVALID, "neddf_field_forward_rays_segment: cone sampling needs >= 2 edges");
+  if (n_rays == 0) return NEDDF_OK;
+  if (!d_ray_dir || !d_ray_orig || !d_dists || !d_density || !d_color)
+    return fail(NEDDF_E_INVALID, "neddf_field_forward_rays_segment: NULL pointer");
+  if ((d_ray_index == nullptr) != (d_n_active == nullptr))
+    return fail(NEDDF_E_INVALID, "neddf_field_forward_rays_segment: d_ray_index and d_n_active go together");
+  FieldParams p = f->proto;
+  int32_t rc = fill_state(f, st, p);
+  if (rc != NEDDF_OK) return rc;
+  p.ray_dir = d_ray_dir; p.ray_orig = d_ray_orig; p.dists = d_dists;
+  p.n_edges = n_edges; p.sampling_type = sampling_type; p.ray_radius = ray_radius;
+  p.n = n_rays * (int64_t)seg_len;  // upper bound: sizes the grid; the kernel reads *d_n_active
+  p.seg_len = seg_len; p.seg_edge0 = edge0; p.ray_index = d_ray_index; p.n_active = d_n_active;
+  p.density = d_density; p.color = d_color;
+  return dispatch(f, p, NEDDF_OUT_EVAL, engine, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------------------------------------
-// training path (fp32 engine)
+// training path
 // ---------------------------------------------------------------------------------------------
 static int32_t fill_rays(const neddf_field* f, const neddf_field_state_t* st, FieldParams& p, const float* d_ray_dir,
                          const float* d_ray_orig, const float* d_dists, int64_t n_rays, int32_t n_edges,

@@ -253,3 +253,66 @@ extern "C" int32_t neddf_composite(const float* d_dists, const float* d_density,
   NEDDF_LAUNCH_CHECK();
   return NEDDF_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// early ray termination: running transmittance after a depth segment, compaction of the live rays
+// ---------------------------------------------------------------------------------------------
+namespace neddf {
+// One thread per listed ray: T *= prod_{j in segment} (1 - o_j + 1e-7), o_j = 1 - exp(-density_j * delta_j)
+// (the factors of base_neural_render.py:148-160), then the ray is kept if T > eps.  Rays are appended with
+// one atomicAdd per warp; their order in the list carries no meaning (outputs are scattered per ray).
+__global__ void terminate_rays_kernel(const float* __restrict__ dists, const float* __restrict__ density, int n_edges,
+                                      int edge0, int seg_len, const int32_t* __restrict__ idx_in,
+                                      const int32_t* __restrict__ n_in, int64_t n_rays, float* __restrict__ trans,
+                                      float eps, int32_t* __restrict__ idx_out, int32_t* __restrict__ n_out,
+                                      unsigned long long* __restrict__ executed) {
+  const int64_t count = idx_in ? (int64_t)(*n_in) : n_rays;
+  if (executed && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(executed, (unsigned long long)(count * seg_len));
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    bool keep = false;
+    int32_t ray = 0;
+    if (i < count) {
+      ray = idx_in ? idx_in[i] : (int32_t)i;
+      const float* d = dists + (int64_t)ray * n_edges;
+      const float* s = density + (int64_t)ray * n_edges;
+      float t = trans[ray];
+      const int e1 = min(edge0 + seg_len, n_edges - 1);  // the last edge only closes the last interval
+      for (int j = edge0; j < e1; ++j) {
+        const float o = 1.0f - expf(-s[j] * (d[j + 1] - d[j]));
+        t *= (1.0f - o + 1e-7f);
+      }
+      trans[ray] = t;
+      keep = t > eps;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(n_out, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) idx_out[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = ray;
+  }
+}
+}  // namespace neddf
+
+extern "C" int32_t neddf_terminate_rays(const float* d_dists, const float* d_density, int64_t n_rays, int32_t n_edges,
+                                        int32_t edge0, int32_t seg_len, const int32_t* d_idx_in,
+                                        const int32_t* d_n_in, float* d_transmittance, float eps, int32_t* d_idx_out,
+                                        int32_t* d_n_out, uint64_t* d_executed, void* stream) {
+  using namespace neddf;
+  if (n_rays < 0 || n_edges < 2 || edge0 < 0 || seg_len < 1 || edge0 + seg_len > n_edges)
+    return fail(NEDDF_E_INVALID, "neddf_terminate_rays: bad sizes");
+  if (n_rays == 0) return NEDDF_OK;
+  if (!d_dists || !d_density || !d_transmittance || !d_idx_out || !d_n_out)
+    return fail(NEDDF_E_INVALID, "neddf_terminate_rays: NULL pointer");
+  if ((d_idx_in == nullptr) != (d_n_in == nullptr)) return fail(NEDDF_E_INVALID, "neddf_terminate_rays: d_idx_in and d_n_in go together");
+  cudaStream_t s = (cudaStream_t)stream;
+  NEDDF_CUDA_CHECK(cudaMemsetAsync(d_n_out, 0, sizeof(int32_t), s));
+  int64_t blocks = (n_rays + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  terminate_rays_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_dists, d_density, n_edges, edge0, seg_len, d_idx_in, d_n_in, n_rays,
+                                                        d_transmittance, eps, d_idx_out, d_n_out,
+                                                        reinterpret_cast<unsigned long long*>(d_executed));
+  NEDDF_LAUNCH_CHECK();
+  return NEDDF_OK;
+}

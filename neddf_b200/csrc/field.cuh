@@ -56,7 +56,13 @@ struct FieldParams {
   int n_edges;
   int sampling_type;
   float ray_radius;
-  int64_t n;  // samples
+  int64_t n;  // samples (upper bound when n_active is given)
+  // segment view for early ray termination: samples [seg_edge0, seg_edge0 + seg_len) of the rays listed in
+  // ray_index[0 .. *n_active) (NULL = rays 0 .. n / seg_len); outputs land at [ray, edge] of the full arrays
+  int seg_len;     // 0 = whole rows
+  int seg_edge0;
+  const int32_t* ray_index;
+  const int32_t* n_active;  // device scalar, read by the kernel (no host synchronisation between segments)
   // outputs (any may be null)
   float* distance;
   float* density;
@@ -67,6 +73,23 @@ struct FieldParams {
   // then the 3 Jacobian rows), written by the fp32 engine when non-null
   float* save_pre;
 };
+
+// number of samples this launch processes / where sample n comes from and where its outputs go
+__device__ __forceinline__ int64_t field_total(const FieldParams& p) {
+  return (p.seg_len > 0 && p.n_active) ? (int64_t)(*p.n_active) * p.seg_len : p.n;
+}
+__device__ __forceinline__ void field_map(const FieldParams& p, int64_t n, int64_t& ray, int& j, int64_t& out) {
+  if (p.seg_len > 0) {
+    const int64_t r = n / p.seg_len;
+    j = p.seg_edge0 + (int)(n - r * p.seg_len);
+    ray = p.ray_index ? (int64_t)p.ray_index[r] : r;
+    out = ray * p.n_edges + j;
+  } else {
+    ray = p.dists ? n / p.n_edges : 0;
+    j = p.dists ? (int)(n % p.n_edges) : 0;
+    out = n;
+  }
+}
 
 // Buffers of the training backward (all device, fp32, row-major)
 struct BackwardIO {

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_simt_kernel(const __grid_co
   const int cg = tid & 15;      // channel group / helper index within the sample
   const int n_hidden = p.n_ddf + p.n_col;
 
-  const int64_t n_tiles = (p.n + kTile - 1) / kTile;
+  const int64_t n_total = field_total(p);
+  const int64_t n_tiles = (n_total + kTile - 1) / kTile;
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - blockIdx.x) / gridDim.x + 1;
   const int64_t total_chunks = my_tiles * p.chunks_per_tile;
@@ -107,15 +108,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_simt_kernel(const __grid_co
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * kTile;
     const int64_t my_n = n0 + s_slot;
-    const bool valid = my_n < p.n;
+    const bool valid = my_n < n_total;
 
     // ---------------- prologue: geometry + embeddings -------------------------------------
     if (cg == 0) {
       float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, var[3] = {0.f, 0.f, 0.f};
       if (valid) {
         if (p.dists) {  // rays + edge distances (ray.py:88-194 fused)
-          int64_t b = my_n / p.n_edges;
-          int j = (int)(my_n % p.n_edges);
+          int64_t b, out_;
+          int j;
+          field_map(p, my_n, b, j, out_);
           const float* row = p.dists + b * p.n_edges;
           float o[3];
 #pragma unroll
@@ -312,15 +314,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_simt_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 3; ++i) colJ[i][c] = colv[1 + i][c];
         }
-        if (p.distance) p.distance[my_n] = h.distance;
-        if (p.density) p.density[my_n] = h.density;
-        if (p.aux_grad) p.aux_grad[my_n] = h.aux;
+        int64_t ray_, on;  // where this sample's outputs go (segment view: [ray, edge] of the full arrays)
+        int j_;
+        field_map(p, my_n, ray_, j_, on);
+        if (p.distance) p.distance[on] = h.distance;
+        if (p.density) p.density[on] = h.density;
+        if (p.aux_grad) p.aux_grad[on] = h.aux;
         if (p.color) {
-          p.color[3 * my_n + 0] = col[0];
-          p.color[3 * my_n + 1] = col[1];
-          p.color[3 * my_n + 2] = col[2];
+          p.color[3 * on + 0] = col[0];
+          p.color[3 * on + 1] = col[1];
+          p.color[3 * on + 2] = col[2];
         }
-        if (p.penalty) p.penalty[my_n] = field_penalty(h, col, colJ, p.distance_range_max, p.penalty_weight);
+        if (p.penalty) p.penalty[on] = field_penalty(h, col, colJ, p.distance_range_max, p.penalty_weight);
       }
     }
     __syncthreads();  // scratch / act are rewritten by the next tile's prologue

@@ -124,13 +124,14 @@ struct TcParams {
 // prologue pieces (epilogue warps)
 // ---------------------------------------------------------------------------------------------
 // geometry of the tile's samples -> scratch (one thread per sample)
-__device__ __forceinline__ void tile_geometry(const FieldParams& p, Scratch* sc, int64_t n0, int s) {
+__device__ __forceinline__ void tile_geometry(const FieldParams& p, Scratch* sc, int64_t n0, int s, int64_t n_total) {
   float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, var[3] = {0.f, 0.f, 0.f};
   const int64_t n = n0 + s;
-  if (n < p.n) {
+  if (n < n_total) {
     if (p.dists) {
-      int64_t b = n / p.n_edges;
-      int j = (int)(n % p.n_edges);
+      int64_t b, out;
+      int j;
+      field_map(p, n, b, j, out);
       const float* row = p.dists + b * p.n_edges;
       float o[3];
 #pragma unroll
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
-  const int64_t n_tiles = (p.n + kTileS - 1) / kTileS;
+  const int64_t n_total = field_total(p);
+  const int64_t n_tiles = (n_total + kTileS - 1) / kTileS;
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - blockIdx.x) / gridDim.x + 1;
   const int64_t total_chunks = my_tiles * P.chunks_per_tile;
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
 
     auto prologue = [&](int64_t tile) {
       const int64_t n0 = tile * kTileS;
-      if (tid < kTileS) tile_geometry(p, sc, n0, tid);
+      if (tid < kTileS) tile_geometry(p, sc, n0, tid, n_total);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const int s = tid >> 4, sub = tid & 15;
       write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 16, true, bad);
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             if (save) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                if (n0 + s0 + i < p.n) save[(size_t)i * 4 * kWidth] = x[i] + bias;
+                if (n0 + s0 + i < n_total) save[(size_t)i * 4 * kWidth] = x[i] + bias;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) tc_hidden_act<ACT>(x[i] + bias, x[i], d1[i]);
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                 if (save) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i)
-                    if (n0 + s0 + i < p.n) save[((size_t)i * 4 + j) * kWidth] = g[i];
+                    if (n0 + s0 + i < n_total) save[((size_t)i * 4 + j) * kWidth] = g[i];
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) split2(d1[2 * i] * g[2 * i], d1[2 * i + 1] * g[2 * i + 1], h[i], l[i], bad);
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             asm volatile("bar.sync 4, 128;" ::: "memory");
             const int s = lane;
             const int64_t n = n0 + s;
-            if (warp == 0 && n < p.n) {
+            if (warp == 0 && n < n_total) {
               const HeadOut& h = sc->head[s];
               float col[3], colJ[3][3];
 #pragma unroll
@@ -522,16 +524,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 3; ++i) colJ[i][c] = sc->hgather[1 + i][s][c];
               }
-              if (p.distance) p.distance[n] = h.distance;
-              if (p.density) p.density[n] = h.density;
-              if (p.aux_grad) p.aux_grad[n] = h.aux;
+              int64_t ray_, on;  // where this sample's outputs go (segment view: [ray, edge] of the full arrays)
+              int j_;
+              field_map(p, n, ray_, j_, on);
+              if (p.distance) p.distance[on] = h.distance;
+              if (p.density) p.density[on] = h.density;
+              if (p.aux_grad) p.aux_grad[on] = h.aux;
               if (p.color) {
-                p.color[3 * n + 0] = col[0];
-                p.color[3 * n + 1] = col[1];
-                p.color[3 * n + 2] = col[2];
+                p.color[3 * on + 0] = col[0];
+                p.color[3 * on + 1] = col[1];
+                p.color[3 * on + 2] = col[2];
               }
               // (in images-only mode the colour Jacobian rows are not computed and no penalty is asked)
-              if (p.penalty) p.penalty[n] = field_penalty(h, col, colJ, p.distance_range_max, p.penalty_weight);
+              if (p.penalty) p.penalty[on] = field_penalty(h, col, colJ, p.distance_range_max, p.penalty_weight);
             }
           }
         }

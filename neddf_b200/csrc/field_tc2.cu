@@ -289,13 +289,14 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-__device__ __forceinline__ void tile_geometry2(const FieldParams& p, Scratch* sc, int64_t n0, int s) {
+__device__ __forceinline__ void tile_geometry2(const FieldParams& p, Scratch* sc, int64_t n0, int s, int64_t n_total) {
   float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, var[3] = {0.f, 0.f, 0.f};
   const int64_t n = n0 + s;
-  if (n < p.n) {
+  if (n < n_total) {
     if (p.dists) {
-      int64_t b = n / p.n_edges;
-      int j = (int)(n % p.n_edges);
+      int64_t b, out;
+      int j;
+      field_map(p, n, b, j, out);
       const float* row = p.dists + b * p.n_edges;
       float o[3];
 #pragma unroll
@@ -361,7 +362,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
   const int64_t cid = blockIdx.x >> 1;
   const int64_t n_clusters = gridDim.x >> 1;
 
-  const int64_t n_tiles = (p.n + kPairS - 1) / kPairS;
+  const int64_t n_total = field_total(p);
+  const int64_t n_tiles = (n_total + kPairS - 1) / kPairS;
   int64_t my_tiles = 0;
   if (cid < n_tiles) my_tiles = (n_tiles - 1 - cid) / n_clusters + 1;
   const int64_t total_chunks = my_tiles * P.chunks_per_tile;
@@ -602,7 +604,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
 
     auto prologue = [&](int64_t tile) {
       const int64_t n0 = tile * kPairS + kTileS * rank;
-      if (tid < kTileS) tile_geometry2(p, sc, n0, tid);
+      if (tid < kTileS) tile_geometry2(p, sc, n0, tid, n_total);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const int s = tid >> 4, sub = tid & 15;
       write_pos_embedding2(p, sc, aux_hi, aux_lo, s, sub, 16, true, bad);
@@ -694,7 +696,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
           if (save) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (ng0 + i < p.n) save[(size_t)i * 4 * kWidth] = x[i] + bias;
+              if (ng0 + i < n_total) save[(size_t)i * 4 * kWidth] = x[i] + bias;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) tc_hidden_act<ACT>(x[i] + bias, x[i], d1[i]);
@@ -747,7 +749,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               if (save) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  if (ng0 + i < p.n) save[((size_t)i * 4 + j) * kWidth] = g[i];
+                  if (ng0 + i < n_total) save[((size_t)i * 4 + j) * kWidth] = g[i];
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) g[i] *= d1[i];
@@ -821,20 +823,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
                 }
               }
             }
-            if (n < p.n) {
+            if (n < n_total) {
               const HeadOut& ho = sc->head[s];
 #pragma unroll
               for (int o = 0; o < 3; ++o) col[o] += __ldg(p.b_head + 2 + o);
-              if (p.distance) p.distance[n] = ho.distance;
-              if (p.density) p.density[n] = ho.density;
-              if (p.aux_grad) p.aux_grad[n] = ho.aux;
+              int64_t ray_, on;  // where this sample's outputs go (segment view: [ray, edge] of the full arrays)
+              int j_;
+              field_map(p, n, ray_, j_, on);
+              if (p.distance) p.distance[on] = ho.distance;
+              if (p.density) p.density[on] = ho.density;
+              if (p.aux_grad) p.aux_grad[on] = ho.aux;
               if (p.color) {
-                p.color[3 * n + 0] = col[0];
-                p.color[3 * n + 1] = col[1];
-                p.color[3 * n + 2] = col[2];
+                p.color[3 * on + 0] = col[0];
+                p.color[3 * on + 1] = col[1];
+                p.color[3 * on + 2] = col[2];
               }
               // (in images-only mode the colour Jacobian rows are not computed and no penalty is asked)
-              if (p.penalty) p.penalty[n] = field_penalty(ho, col, colJ, p.distance_range_max, p.penalty_weight);
+              if (p.penalty) p.penalty[on] = field_penalty(ho, col, colJ, p.distance_range_max, p.penalty_weight);
             }
           }
         }

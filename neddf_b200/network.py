@@ -434,6 +434,29 @@ class NeDDF(BaseNeuralField):
             prof.append((e0, e1, B * S))
         return out
 
+    def forward_rays_segment(self, ray_dir: Tensor, ray_orig: Tensor, dists: Tensor, sampling_type: str, ray_radius: float,
+                             edge0: int, seg_len: int, ray_index: Optional[Tensor], n_active: Optional[Tensor],
+                             density: Tensor, color: Tensor) -> None:
+        """One depth segment of the fine pass for early ray termination (neddf_field_forward_rays_segment):
+        samples [edge0, edge0 + seg_len) of the rays listed in ``ray_index[:n_active]`` (device tensors, None =
+        all rays); results are scattered into ``density`` [B,E] / ``color`` [B,E,3] in place.  No-grad only."""
+        B, E = dists.shape
+        device = dists.device
+        h = self._field(device)
+        st = self._state_struct()
+        prof = self._profile_events
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(device))
+        with torch.cuda.device(device):
+            L.check(L.lib().neddf_field_forward_rays_segment(
+                h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, E, L.SAMPLING_IDS[sampling_type],
+                float(ray_radius), int(edge0), int(seg_len), L.ptr(ray_index), L.ptr(n_active), L.ptr(density),
+                L.ptr(color), L.ENGINE_IDS[self.engine], L.stream_ptr(device)), "field_forward_rays_segment")
+        if prof is not None:
+            e1.record(torch.cuda.current_stream(device))
+            prof.append((e0, e1, None))  # the executed count lives on the device (NeRFRender.termination_stats)
+
     def check_engine_status(self) -> None:
         """Read-and-clear the engine's device status word (one sync).  Raises if the tensor-core
         engine met an activation outside fp16 range (its operands are fp16 hi+lo pairs)."""

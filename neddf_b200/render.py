@@ -247,6 +247,13 @@ class NeRFRender(BaseNeuralRender):
         self.check_nan = True
         # rays per internal launch in render_image (bounds the [rays, samples] work buffers)
         self.image_chunk = 65536
+        # Early ray termination (BASELINE.json configs[4]; NOT in the reference, so opt-in): in no-grad image
+        # renders the fine pass runs in `termination_segments` depth segments and a ray stops being evaluated
+        # once its transmittance falls to `transmittance_eps`.  0.0 = off = the reference's behaviour, bit for
+        # bit.  Error bound: |d color| <= eps * max|c|, |d depth| <= eps * max_dist, |d transmittance| <= eps.
+        self.transmittance_eps = 0.0
+        self.termination_segments = 4
+        self._term_counters = None
 
     # ------------------------------------------------------------------ module surface --
     def get_network(self) -> BaseNeuralField:
@@ -291,12 +298,56 @@ class NeRFRender(BaseNeuralRender):
                                               need_penalty=full, need_aux=False)
         ic = self.integrate_volume_render(dists_c, vc["density"], vc["color"], vc.get("fields_penalty"))
         dists_f = self.sample_pdf(dists_c, ic["weight"], Ef_new, uniform_rands=u_fine)
-        vf = self.network_fine.forward_rays(ray_dir, ray_orig, dists_f, self.sampling_type, self._ray_radius,
-                                            need_penalty=full, need_aux=False)
+        if not full and self.transmittance_eps > 0.0 and not torch.is_grad_enabled():
+            vf = self._fine_pass_terminated(ray_dir, ray_orig, dists_f)
+        else:
+            vf = self.network_fine.forward_rays(ray_dir, ray_orig, dists_f, self.sampling_type, self._ray_radius,
+                                                need_penalty=full, need_aux=False)
         out = self.integrate_volume_render(dists_f, vf["density"], vf["color"], vf.get("fields_penalty"))
         for k in list(ic.keys()):
             out[k + "_coarse"] = ic[k]
         return out
+
+    def _fine_pass_terminated(self, ray_dir: Tensor, ray_orig: Tensor, dists_f: Tensor) -> Dict[str, Tensor]:
+        """Fine pass with early ray termination: evaluate a depth segment, update every live ray's
+        transmittance, keep the rays with T > eps, continue.  Everything stays on the device (the live-ray
+        count is read by the next kernel, not by the host).  Samples that are never evaluated keep density 0
+        and so drop out of the compositing sum (base_neural_render.py:148-172 with o_j = 0)."""
+        lib = L.lib()
+        B, E = dists_f.shape
+        device = dists_f.device
+        density = torch.zeros(B, E, device=device, dtype=torch.float32)
+        color = torch.zeros(B, E, 3, device=device, dtype=torch.float32)
+        trans = torch.ones(B, device=device, dtype=torch.float32)
+        idx = [torch.empty(B, device=device, dtype=torch.int32) for _ in range(2)]
+        cnt = [torch.zeros(1, device=device, dtype=torch.int32) for _ in range(2)]
+        if self._term_counters is None or self._term_counters.device != device:
+            self._term_counters = torch.zeros(2, device=device, dtype=torch.int64)  # executed, nominal
+        executed = self._term_counters[0:1]
+        self._term_counters[1] += B * E
+        K = max(1, min(int(self.termination_segments), E))
+        bounds = [round(k * E / K) for k in range(K + 1)]
+        cur_idx, cur_n = None, None
+        stream = L.stream_ptr(device)
+        for k in range(K):
+            e0, seg = bounds[k], bounds[k + 1] - bounds[k]
+            self.network_fine.forward_rays_segment(ray_dir, ray_orig, dists_f, self.sampling_type, self._ray_radius, e0, seg,
+                                                   cur_idx, cur_n, density, color)
+            L.check(lib.neddf_terminate_rays(L.ptr(dists_f), L.ptr(density), B, E, e0, seg, L.ptr(cur_idx), L.ptr(cur_n),
+                                             L.ptr(trans), float(self.transmittance_eps), L.ptr(idx[k % 2]),
+                                             L.ptr(cnt[k % 2]), L.ptr(executed), stream), "terminate_rays")
+            cur_idx, cur_n = idx[k % 2], cnt[k % 2]
+        return {"density": density, "color": color}
+
+    def termination_stats(self, reset: bool = True) -> Dict[str, int]:
+        """MLP evaluations of the fine passes since the last call: executed (after early termination) and
+        nominal (what the reference would have run).  One device synchronisation."""
+        if self._term_counters is None:
+            return {"executed": 0, "nominal": 0}
+        e, n = (int(v) for v in self._term_counters.tolist())
+        if reset:
+            self._term_counters.zero_()
+        return {"executed": e, "nominal": n}
 
     def _uniforms(self, B: int, device, uniforms) -> Tuple[Tensor, Tensor]:
         Ec, Ef = self.sample_coarse + 1, self.sample_fine + 1

@@ -14,6 +14,7 @@ from tests.helpers import PARITY_TOL, Case, assert_parity, nerr  # noqa: E402
 
 CASES = ["bunny", "default", "point", "leaky"]
 ENGINES = ["fp32", "tc", "tc2"]
+GRAD_TOL = 1e-4  # north_star: 1e-4 rel fp32, gradients included
 
 
 def _gpu():
@@ -525,7 +526,9 @@ def test_field_backward_matches_autograd(name, engine):
             obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
         got = getattr(obj, attr).grad
         assert got is not None, k
-        assert nerr(got.cpu().numpy(), v.grad.numpy()) < 2e-3, k
+        # measured (tools/grad_err.py): 1.6e-6 .. 3.5e-5 against the fp64 arbiter on all three engines; the
+        # fp32 reference itself sits at 1e-6 .. 1e-5 of fp64 (tests/test_oracle_derivatives.py)
+        assert nerr(got.cpu().numpy(), v.grad.numpy()) < GRAD_TOL, k
 
 
 def test_render_rays_training_matches_reference_gradients():
@@ -554,7 +557,7 @@ def test_render_rays_training_matches_reference_gradients():
         g = p.grad.cpu().numpy()
         if g.ndim == 2 and g.shape[1] > 3:
             g = g[::8]
-        assert nerr(g, ref) < 2e-3, name
+        assert nerr(g, ref) < 2 * GRAD_TOL, name  # end to end: resampled positions move with the coarse weights
         checked += 1
     assert checked == 26
 
@@ -590,7 +593,7 @@ def test_network_forward_sampling_is_differentiable():
         obj = net
         for part in mod.split("."):
             obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
-        assert nerr(getattr(obj, attr).grad.cpu().numpy(), Pg[k].grad.numpy()) < 2e-3, k
+        assert nerr(getattr(obj, attr).grad.cpu().numpy(), Pg[k].grad.numpy()) < GRAD_TOL, k
 
 
 def test_other_embedding_ranks_run_on_a_tensor_core_engine():
@@ -620,3 +623,79 @@ def test_other_embedding_ranks_run_on_a_tensor_core_engine():
     for k in ("distance", "density", "color", "fields_penalty", "aux_grad"):
         assert nerr(out[k].cpu().numpy(), ref[k].numpy()) < PARITY_TOL, k
     net.check_engine_status()
+
+
+@pytest.mark.parametrize("engine", ["tc", "tc2", "fp32"])
+def test_early_ray_termination(engine):
+    """Opt-in early ray termination of the fine pass (BASELINE.json configs[4]; the reference has none):
+    off = the normal path; one segment = the segment kernel on all samples = bit-identical outputs; on =
+    bounded error (|d color| <= eps max|c|, |d depth| <= eps max_dist, |d T| <= eps) and fewer evaluations."""
+    G = _gpu()
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "case_image.npz"))
+    c = Case("bunny")
+    render, cam = G.build_render(c, engine), G.build_camera(c)
+    w, h, ds = int(z["width"]), int(z["height"]), int(z["downsampling"])
+    n_pix = (w // ds) * (h // ds)
+    g = torch.Generator().manual_seed(int(z["rand_seed"]))
+    u = (torch.rand(n_pix, 65, generator=g).to(G.DEV), torch.rand(n_pix, 129, generator=g).to(G.DEV))
+    keys = ["color", "depth", "transmittance"]
+    base = render.render_image(w, h, cam, keys, ds, uniforms=u)
+    assert render.termination_stats() == {"executed": 0, "nominal": 0}
+    render.transmittance_eps, render.termination_segments = 1e-30, 1  # one segment: nothing can stop early
+    one = render.render_image(w, h, cam, keys, ds, uniforms=u)
+    st = render.termination_stats()
+    assert st["executed"] == st["nominal"] > 0
+    for k in keys:
+        assert torch.equal(one[k], base[k]), k
+    cmax = float(base["color"].abs().max())
+    saved = []
+    for eps in (1e-3, 5e-2):  # (the smoke bunny is translucent: few rays ever get below 1e-3)
+        render.transmittance_eps, render.termination_segments = eps, 6
+        out = render.render_image(w, h, cam, keys, ds, uniforms=u)
+        st = render.termination_stats()
+        assert 0 < st["executed"] <= st["nominal"], st
+        saved.append(1.0 - st["executed"] / st["nominal"])
+        assert float((out["color"] - base["color"]).abs().max()) <= eps * cmax * 1.05 + 1e-6
+        assert float((out["depth"] - base["depth"]).abs().max()) <= eps * render.max_dist * 1.05 + 1e-6
+        assert float((out["transmittance"] - base["transmittance"]).abs().max()) <= eps * 1.05
+    assert saved[1] >= saved[0] > 0.0, saved
+    render.check_status()
+
+
+def test_terminate_rays_kernel():
+    """neddf_terminate_rays on a synthetic wall: transmittance update = the compositing factors
+    (base_neural_render.py:148-160), kept rays = exactly those with T > eps, executed-evaluation counter."""
+    G = _gpu()
+    from neddf_b200 import _lib as L
+    g = torch.Generator().manual_seed(8)
+    B, E = 1000, 40
+    dists = torch.sort(torch.rand(B, E, generator=g) * 4 + 2, dim=1).values
+    dens = torch.rand(B, E, generator=g) * 0.3
+    dens[::3, 10:14] = 80.0  # an opaque wall on every third ray
+    o = 1 - torch.exp(-dens[:, :-1] * (dists[:, 1:] - dists[:, :-1]))
+    fac = 1 - o + 1e-7
+    dd, sd = dists.to(G.DEV), dens.to(G.DEV)
+    trans = torch.ones(B, device=G.DEV)
+    idx = [torch.full((B,), -1, dtype=torch.int32, device=G.DEV) for _ in range(2)]
+    cnt = [torch.zeros(1, dtype=torch.int32, device=G.DEV) for _ in range(2)]
+    ex = torch.zeros(1, dtype=torch.int64, device=G.DEV)
+    eps = 1e-2
+    cur_i, cur_n, live, expect_ex = None, None, torch.ones(B, dtype=torch.bool), 0
+    T = torch.ones(B)
+    for k, (e0, seg) in enumerate(((0, 12), (12, 12), (24, 16))):
+        L.check(L.lib().neddf_terminate_rays(L.ptr(dd), L.ptr(sd), B, E, e0, seg, L.ptr(cur_i), L.ptr(cur_n), L.ptr(trans), eps,
+                                             L.ptr(idx[k % 2]), L.ptr(cnt[k % 2]), L.ptr(ex), L.stream_ptr(G.DEV)))
+        torch.cuda.synchronize()
+        expect_ex += int(live.sum()) * seg
+        e1 = min(e0 + seg, E - 1)
+        T = torch.where(live, T * fac[:, e0:e1].prod(1), T)
+        live = live & (T > eps)
+        n = int(cnt[k % 2].item())
+        kept = torch.sort(idx[k % 2][:n].cpu().long()).values
+        assert torch.equal(kept, torch.nonzero(live).flatten()), k
+        assert nerr(trans.cpu().numpy(), T.numpy()) < 1e-5
+        cur_i, cur_n = idx[k % 2], cnt[k % 2]
+    assert int(ex.item()) == expect_ex
+    assert int((~live).sum()) >= B // 3  # the walls stopped their rays
