@@ -458,6 +458,10 @@ def main():
                          "(1024-ray training step: forward + backward + Adam)")
     ap.add_argument("--cpu-rays", type=int, default=384, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eps", type=float, default=0.0,
+                    help="early ray termination threshold on the transmittance (BASELINE.json configs[4]; 0 = off = "
+                         "the reference's behaviour, the default workload)")
+    ap.add_argument("--segments", type=int, default=4, help="depth segments of the fine pass when --eps > 0")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rules: W >= 3
@@ -491,6 +495,7 @@ def main():
     render.set_iter(-1)
     render.set_engine(args.engine)
     render.check_nan = False  # no host sync inside the timed region; checked once after it
+    render.transmittance_eps, render.termination_segments = float(args.eps), int(args.segments)
     n_pix = W * H
     first, count = shard_range(n_pix, world, rank)
     n_frames = n_gpus  # frames per step
@@ -567,11 +572,17 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    render.termination_stats()  # reset the executed / nominal counters after the warm-up
     launches0 = L.lib().neddf_launch_count()
     ms_total, evs = timed(step_device, args.steps, profile=True)
     launches = L.lib().neddf_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     render.check_status()
+    term = render.termination_stats()  # fine-pass evaluations of this rank inside the timed region
+    if world > 1:
+        tt = torch.tensor([term["executed"], term["nominal"]], device=dev, dtype=torch.int64)
+        dist.all_reduce(tt)
+        term = {"executed": int(tt[0]), "nominal": int(tt[1])}
     ms_step = ms_total / args.steps
     rays_per_step = n_pix * n_frames
     value = rays_per_step * NOMINAL_PER_RAY / (ms_step * 1e-3)
@@ -581,7 +592,9 @@ def main():
     evals, kms = 0, 0.0
     for (e0, e1, n_eval) in evs:
         kms += e0.elapsed_time(e1)
-        evals += n_eval
+        evals += n_eval or 0
+    if args.eps > 0:  # segment launches carry no static count: coarse passes + what the fine passes really ran
+        evals = args.steps * n_frames * count * (S_COARSE + 1) + term["executed"] // world
     flop = F_EVAL
     achieved_tflops = evals * flop / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
     peaks = {}
@@ -632,6 +645,11 @@ def main():
                          "kernel_share_of_step": kms / ms_total if ms_total else None},
             "cpu_baseline": cpu,
             "parity": parity,
+            "early_termination": None if args.eps <= 0 else {
+                "transmittance_eps": args.eps, "segments": args.segments,
+                "fine_evaluations_executed": term["executed"], "fine_evaluations_nominal": term["nominal"],
+                "note": "value / e2e count NOMINAL ray-samples; executed < nominal is work skipped under the error bound "
+                        "|d color| <= eps max|c| (not in the reference: opt-in)"},
             "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),

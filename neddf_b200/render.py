@@ -50,13 +50,26 @@ def _instantiate(network_config) -> BaseNeuralField:
 
 
 def _camera_host(camera) -> Tuple[Any, Any, Any]:
-    """R[9], T[3], calib[4] as ctypes float arrays (one small D2H per call)."""
-    R = camera.R.detach().to("cpu", torch.float32).reshape(-1).tolist()
-    T = camera.T.detach().to("cpu", torch.float32).reshape(-1).tolist()
-    calib = camera.camera_calib.params.detach().to("cpu", torch.float32).reshape(-1).tolist()
-    if len(R) != 9 or len(T) != 3 or len(calib) < 4:
+    """R[9], T[3], calib[4] as ctypes float arrays.  The three tensors are read back ONCE per camera state:
+    the result is cached on the camera object and keyed by the tensors' identity and version counters
+    (Camera.update_transform rebinds R / T; in-place edits bump _version), so a training loop that renders
+    from the same pose pays no device synchronisation per step."""
+    R_t, T_t, C_t = camera.R, camera.T, camera.camera_calib.params
+    key = tuple((id(x), x.data_ptr(), x._version) for x in (R_t, T_t, C_t))
+    cached = getattr(camera, "_neddf_b200_host", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    flat = torch.cat([R_t.detach().reshape(-1).to(torch.float32), T_t.detach().reshape(-1).to(torch.float32),
+                      C_t.detach().reshape(-1).to(torch.float32)]).to("cpu").tolist()  # one D2H copy
+    nR, nT = R_t.numel(), T_t.numel()
+    if nR != 9 or nT != 3 or len(flat) - 12 < 4:
         raise ValueError("camera must expose R[3,3], T[3] and camera_calib.params=[fx,fy,cx,cy]")
-    return L.fbuf(R), L.fbuf(T), L.fbuf(calib[:4])
+    out = (L.fbuf(flat[:9]), L.fbuf(flat[9:12]), L.fbuf(flat[12:16]))
+    try:
+        camera._neddf_b200_host = (key, out)
+    except Exception:  # objects that refuse new attributes just pay the copy every time
+        pass
+    return out
 
 
 class _CompositeFn(torch.autograd.Function):
