@@ -119,6 +119,18 @@ int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* 
  * issue done, epilogue start, epilogue done.  Pass NULL to switch it off. */
 int32_t neddf_field_set_timeline(neddf_field_t* f, int64_t* d_buf, int32_t capacity);
 
+/* Weight gradients of LinearGradFunction.backward (nn_module/with_grad/linear.py:72-80) as a tensor-core
+ * split-K GEMM with fp16 hi/lo operands split on the fly (3 products, fp32 accumulation, deterministic):
+ *     out[m, n] = sum_r A[r, a_col0 + m] * B[r, n],   m < ka <= 128,  n < n_cols <= 256
+ * A: [rows, lda] fp32 (layer inputs X, or the head gradients), B: [rows, ldb] fp32 with 256 columns (the
+ * pre-activation gradients G, or the last hidden activations).  d_workspace: neddf_wgrad_workspace_bytes(). */
+int64_t neddf_wgrad_workspace_bytes(void);
+int32_t neddf_wgrad(const float* d_a, int64_t lda, int32_t a_col0, int32_t ka, const float* d_b, int64_t ldb,
+                    int64_t rows, float* d_out, int64_t ld_out, int32_t n_cols, float* d_workspace, void* stream);
+/* Bias gradients (linear.py:80): out[c] = sum over samples of G[sample][0][c] (value rows of [n,4,256]). */
+int32_t neddf_colsum_value_rows(const float* d_g, int64_t n_samples, int64_t sample_stride, float* d_out,
+                                float* d_workspace, void* stream);
+
 /* Early ray termination (BASELINE.json configs[4]; opt-in, not in the reference whose compositing visits every
  * sample, base_neural_render.py:148-172).  The field on ONE depth segment: samples [edge0, edge0+seg_len) of the
  * rays listed in d_ray_index[0 .. *d_n_active) (both NULL = all n_rays rays); density / colour are scattered to

@@ -46,8 +46,9 @@ class _FieldTrainFn(torch.autograd.Function):
               tensor-core by default, "fp32" on request), keeping every layer's pre-activations.
     backward: neddf_field_backward does all sample-local work (activation second derivatives, heads,
               density, penalties, data-gradient GEMMs) and writes per-layer inputs X_l and
-              pre-activation gradients G_l; the weight gradients gW_l = X_l^T G_l are plain GEMMs over
-              all samples (cuBLAS through torch.matmul), bias gradients column sums.
+              pre-activation gradients G_l; the weight gradients gW_l = X_l^T G_l are tensor-core split-K
+              GEMMs of this library (neddf_wgrad, csrc/wgrad.cu), bias gradients column sums
+              (neddf_colsum_value_rows).
     Gradients flow to the module's parameters only (sample positions come from torch.rand / a
     no_grad resampling in the reference, nerf_render.py:131-166).
     """
@@ -131,28 +132,53 @@ class _FieldTrainFn(torch.autograd.Function):
                     L.ptr(g_color), L.ptr(g_penalty), L.ptr(post), L.ptr(gpre), L.ptr(ghead_da), L.ptr(ghead_col),
                     L.ptr(xes), L.ptr(xcol), L.stream_ptr(device)), "field_backward_samples")
 
-        # weight gradients: gW = X^T G over the 4N rows (linear.py:76-79), bias = sum over value rows
-        def wgrad(parts, G):
-            G2 = G.reshape(4 * n, -1)
-            return torch.cat([x.reshape(4 * n, -1).t() @ G2 for x in parts], 0)
+        # weight gradients gW = X^T G over the 4N rows (linear.py:76-79) and bias gradients (sum over the value
+        # rows): tensor-core split-K GEMMs of this library (csrc/wgrad.cu), written straight into the gradient
+        # tensors - no library GEMM on the training path
+        lib = L.lib()
+        stream = L.stream_ptr(device)
+        ws = getattr(net, "_wgrad_ws", None)
+        if ws is None or ws.device != device:
+            ws = torch.empty(int(lib.neddf_wgrad_workspace_bytes()) // 4, device=device, dtype=torch.float32)
+            net._wgrad_ws = ws
+        R = 4 * n
+
+        def wgrad_into(out, row0, A, lda, ka, Bm, n_cols=256):
+            """out[row0 : row0 + ka, :n_cols] = A[:, :ka]^T Bm, in 128-column tiles of A."""
+            for c0 in range(0, ka, 128):
+                kk = min(128, ka - c0)
+                L.check(lib.neddf_wgrad(L.ptr(A), lda, c0, kk, L.ptr(Bm), 256, R,
+                                        C.c_void_p(out.data_ptr() + 4 * (row0 + c0) * out.shape[1]), out.shape[1], n_cols,
+                                        L.ptr(ws), stream), "wgrad")
 
         grads = []
-        for l in range(n_hidden):
-            if l == 0:
-                parts = [xes]
-            elif l < n_ddf:
-                parts = ([xes] if (l - 1) in net.skips else []) + [post[l - 1]]
-            elif l == n_ddf:
-                parts = [xcol, post[n_ddf - 1]]
-            else:
-                parts = [post[l - 1]]
-            grads.append(wgrad(parts, gpre[l]))
-            grads.append(gpre[l][:, 0, :].sum(0))
-        g_da = wgrad([post[n_ddf - 1]], ghead_da)           # [256, 2]
+        with torch.cuda.device(device):
+            for l in range(n_hidden):
+                if l == 0:
+                    parts = [(xes, n_e0)]
+                elif l < n_ddf:
+                    parts = ([(xes, n_e0)] if (l - 1) in net.skips else []) + [(post[l - 1], 256)]
+                elif l == n_ddf:
+                    parts = [(xcol, off_h), (post[n_ddf - 1], 256)]
+                else:
+                    parts = [(post[l - 1], 256)]
+                gW = torch.empty(sum(k for _, k in parts), 256, device=device, dtype=torch.float32)
+                row0 = 0
+                for X, k_in in parts:
+                    wgrad_into(gW, row0, X, k_in, k_in, gpre[l])
+                    row0 += k_in
+                gb = torch.empty(256, device=device, dtype=torch.float32)
+                L.check(lib.neddf_colsum_value_rows(L.ptr(gpre[l]), n, 4 * 256, L.ptr(gb), L.ptr(ws), stream), "colsum")
+                grads += [gW, gb]
+            # heads: gW^T [outs, 256] = ghead^T post (the 2- / 3-column head gradients are the A operand)
+            gda_t = torch.empty(2, 256, device=device, dtype=torch.float32)
+            wgrad_into(gda_t, 0, ghead_da, 2, 2, post[n_ddf - 1])
+            gc_t = torch.empty(3, 256, device=device, dtype=torch.float32)
+            wgrad_into(gc_t, 0, ghead_col, 4, 3, post[n_hidden - 1])
         b_da = ghead_da[:, 0, :].sum(0)
-        grads += [g_da[:, 0:1].contiguous(), b_da[0:1].contiguous(), g_da[:, 1:2].contiguous(), b_da[1:2].contiguous()]
-        g_c = wgrad([post[n_hidden - 1]], ghead_col)[:, :3]
-        grads += [g_c.contiguous(), ghead_col[:, 0, :3].sum(0)]
+        grads += [gda_t[0].reshape(256, 1).contiguous(), b_da[0:1].contiguous(), gda_t[1].reshape(256, 1).contiguous(),
+                  b_da[1:2].contiguous()]
+        grads += [gc_t.t().contiguous(), ghead_col[:, 0, :3].sum(0)]
         return (None, None, None, None, None, None) + tuple(grads)
 
 

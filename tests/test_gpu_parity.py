@@ -699,3 +699,34 @@ def test_terminate_rays_kernel():
         cur_i, cur_n = idx[k % 2], cnt[k % 2]
     assert int(ex.item()) == expect_ex
     assert int((~live).sum()) >= B // 3  # the walls stopped their rays
+
+
+@pytest.mark.parametrize("rows,lda,col0,ka", [(4096, 256, 0, 128), (100003, 256, 128, 128), (7777, 60, 0, 60), (5000, 87, 0, 87),
+                                              (9001, 2, 0, 2), (6000, 4, 0, 3)])
+def test_wgrad_gemm(rows, lda, col0, ka):
+    """neddf_wgrad (tcgen05 split-K GEMM, fp16 hi/lo operands split on the fly) against an fp64 matmul:
+    the shapes of the training backward (aligned / ragged / 2- and 3-column head operands, slab remainders)."""
+    G = _gpu()
+    from neddf_b200 import _lib as L
+    g = torch.Generator().manual_seed(rows + ka)
+    A = torch.randn(rows, lda, generator=g)
+    B = torch.randn(rows, 256, generator=g)
+    A[5 % rows, col0] = 300.0
+    Ad, Bd = A.to(G.DEV), B.to(G.DEV)
+    out = torch.full((ka, 256), float("nan"), device=G.DEV)
+    ws = torch.empty(int(L.lib().neddf_wgrad_workspace_bytes()) // 4, device=G.DEV)
+    L.check(L.lib().neddf_wgrad(L.ptr(Ad), lda, col0, ka, L.ptr(Bd), 256, rows, L.ptr(out), 256, 256, L.ptr(ws),
+                                L.stream_ptr(G.DEV)), "wgrad")
+    out2 = torch.empty_like(out)
+    L.check(L.lib().neddf_wgrad(L.ptr(Ad), lda, col0, ka, L.ptr(Bd), 256, rows, L.ptr(out2), 256, 256, L.ptr(ws),
+                                L.stream_ptr(G.DEV)), "wgrad")
+    torch.cuda.synchronize()
+    ref = A[:, col0:col0 + ka].double().t() @ B.double()
+    err = float((out.cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err  # fp32 accumulation over up to 1e5 rows (the split operands themselves are good to 2e-7)
+    assert torch.equal(out, out2)  # fixed summation order
+    gsum = torch.empty(256, device=G.DEV)
+    n_s = rows // 4
+    L.check(L.lib().neddf_colsum_value_rows(L.ptr(Bd), n_s, 4 * 256, L.ptr(gsum), L.ptr(ws), L.stream_ptr(G.DEV)), "colsum")
+    refs = B[:4 * n_s].reshape(n_s, 4, 256)[:, 0, :].double().sum(0)
+    assert float((gsum.cpu().double() - refs).abs().max() / refs.abs().max()) < 1e-5
