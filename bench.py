@@ -367,7 +367,9 @@ def run_train(args):
     R, T, calib = synthetic_pose(0)
     cam = neddf_b200.Camera.from_matrix(neddf_b200.PinholeCalib(calib), R, T).to(dev)
     cam.update_transform()
-    opt = torch.optim.Adam(render.get_parameters_list(), lr=TRAIN_LR)
+    from neddf_b200 import losses, optim
+    opt = optim.FusedAdam.for_render(render, lr=TRAIN_LR)          # one launch per network + re-pack
+    loss_fn = losses.RenderLoss(**{k: v for k, v in LOSS_W.items()})  # the six loss terms in one launch
     n_batches = 8
     host = [tuple(x.pin_memory() for x in train_batch(i, TRAIN_RAYS)) for i in range(n_batches)]
     resident = [tuple(x.to(dev) for x in b) for b in host]
@@ -377,7 +379,7 @@ def run_train(args):
         render.set_iter(it[0])
         it[0] += 1
         out = render.render_rays(uv, cam)
-        loss = train_loss(out, color, mask)
+        loss = torch.sum(torch.stack(list(loss_fn(out, {"color": color, "mask": mask}).values())))  # nerf_trainer.py:121
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()

@@ -119,6 +119,26 @@ int32_t neddf_field_status(const neddf_field_t* f, int32_t* h_status_out, void* 
  * issue done, epilogue start, epilogue done.  Pass NULL to switch it off. */
 int32_t neddf_field_set_timeline(neddf_field_t* f, int64_t* d_buf, int32_t capacity);
 
+/* The reference's training objective in one launch (loss/base_loss.py:45-85, color_loss.py:41-55,
+ * mask_bce_loss.py:41-59, fields_constraint_loss.py:40-54; summed as nerf_trainer.py:118-121):
+ *   d_weights[6] = weight, weight_coarse of ColorLoss, MaskBCELoss, FieldsConstraintLoss (0 = term off)
+ *   d_terms[6]   = the six weighted terms (device); g_* = gradients of their SUM w.r.t. the render outputs
+ * Any input / gradient pointer may be NULL when its weight is 0. */
+int32_t neddf_render_loss(const float* d_color, const float* d_color_coarse, const float* d_trans,
+                          const float* d_trans_coarse, const float* d_penalty, const float* d_penalty_coarse,
+                          const float* d_target_color, const float* d_target_mask, int64_t n_rays,
+                          const float* d_weights, float* d_terms, float* g_color, float* g_color_coarse,
+                          float* g_trans, float* g_trans_coarse, float* g_penalty, float* g_penalty_coarse,
+                          void* stream);
+
+/* torch.optim.Adam step of n_tensors parameter tensors in one launch (nerf_trainer.py:38-42, 129); with a
+ * field handle the tensors must be (weight, bias) of every layer in reference order and the kernel-layout
+ * weights are re-packed on the same stream (what neddf_field_set_weights does after every optimiser step). */
+int32_t neddf_field_adam_step(neddf_field_t* f, float* const* d_params, const float* const* d_grads,
+                              float* const* d_exp_avg, float* const* d_exp_avg_sq, const int64_t* h_numel,
+                              int32_t n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              int64_t step, void* stream);
+
 /* Weight gradients of LinearGradFunction.backward (nn_module/with_grad/linear.py:72-80) as a tensor-core
  * split-K GEMM with fp16 hi/lo operands split on the fly (3 products, fp32 accumulation, deterministic):
  *     out[m, n] = sum_r A[r, a_col0 + m] * B[r, n],   m < ka <= 128,  n < n_cols <= 256

@@ -4,6 +4,7 @@ from .camera import Camera, PinholeCalib  # noqa: F401
 from .network import BaseNeuralField, LinearGradLayer, NeDDF  # noqa: F401
 from .ray import CONE_RAY_RADIUS, Ray, Sampling  # noqa: F401
 from .render import BaseNeuralRender, NeRFRender  # noqa: F401
+from . import losses, optim  # noqa: F401
 
 __all__ = ["NeRFRender", "NeDDF", "BaseNeuralRender", "BaseNeuralField", "LinearGradLayer", "Ray", "Sampling",
            "Camera", "PinholeCalib", "CONE_RAY_RADIUS"]

@@ -63,6 +63,9 @@ _SIGNATURES = {
     "neddf_field_forward": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _P]),
     "neddf_field_forward_rays": (_I32, [_P, C.POINTER(FieldState), _P, _P, _P, _I64, _I32, _I32, _F,
                                         _P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "neddf_render_loss": (_I32, [_P] * 8 + [_I64] + [_P] * 8 + [_P]),
+    "neddf_field_adam_step": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_I64), _I32,
+                                     _F, _F, _F, _F, _F, _I64, _P]),
     "neddf_wgrad_workspace_bytes": (_I64, []),
     "neddf_wgrad": (_I32, [_P, _I64, _I32, _I32, _P, _I64, _I64, _P, _I64, _I32, _P, _P]),
     "neddf_colsum_value_rows": (_I32, [_P, _I64, _I64, _P, _P, _P]),

@@ -16,7 +16,8 @@ import importlib
 
 def install(patch_trainer: bool = False) -> None:
     """Rebind the reference's render / network classes; with ``patch_trainer`` also replace
-    ``BaseTrainer.construct_ground_truth`` by the vectorised gather of ``neddf_b200.trainer_glue``."""
+    ``BaseTrainer.construct_ground_truth`` by the vectorised gather of ``neddf_b200.trainer_glue`` and the three
+    loss classes of ``neddf.loss`` by the fused-kernel ones of ``neddf_b200.losses``."""
     import neddf_b200
 
     ref_render = importlib.import_module("neddf.render")
@@ -30,7 +31,12 @@ def install(patch_trainer: bool = False) -> None:
         except Exception:
             pass
     if patch_trainer:
-        from neddf_b200 import trainer_glue
+        from neddf_b200 import losses, trainer_glue
 
         base_trainer = importlib.import_module("neddf.trainer.base_trainer")
         base_trainer.BaseTrainer.construct_ground_truth = trainer_glue.construct_ground_truth
+        # the loss classes hydra instantiates from config/loss/*.yaml (`_target_: neddf.loss.ColorLoss` ...):
+        # same constructors and call signature, one CUDA launch each instead of ~10 element-wise kernels
+        ref_loss = importlib.import_module("neddf.loss")
+        for name in ("ColorLoss", "MaskBCELoss", "FieldsConstraintLoss"):
+            setattr(ref_loss, name, getattr(losses, name))
