@@ -258,37 +258,6 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src,
                : "memory");
 }
 
-// Sum v[i] over the 32 lanes of the warp for N values per lane; afterwards lane L holds the totals of
-// indices [L * N / 32, (L + 1) * N / 32) in v[0 .. N/32).  N / 32 * 31 shuffles instead of 5 N.
-template <int N>
-__device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane) {
-#pragma unroll
-  for (int d = 16, n = N / 2; d >= 1; d >>= 1, n >>= 1) {
-    const bool upper = (lane & d) != 0;
-#pragma unroll
-    for (int t = 0; t < n; ++t) {
-      const float send = upper ? v[t] : v[t + n];
-      const float keep = upper ? v[t + n] : v[t];
-      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, d);
-    }
-  }
-}
-
-// N = 16: lane L ends with the total of index L >> 1 (both lanes of a pair hold it)
-__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int d = 16, n = 8; d >= 2; d >>= 1, n >>= 1) {
-    const bool upper = (lane & d) != 0;
-#pragma unroll
-    for (int t = 0; t < n; ++t) {
-      const float send = upper ? v[t] : v[t + n];
-      const float keep = upper ? v[t + n] : v[t];
-      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, d);
-    }
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 __device__ __forceinline__ void tile_geometry2(const FieldParams& p, Scratch* sc, int64_t n0, int s, int64_t n_total) {
   float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, var[3] = {0.f, 0.f, 0.f};
   const int64_t n = n0 + s;
