@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     const int ch = 128 * half + 32 * quarter + lane;
     const uint32_t lane_addr = (uint32_t)(32 * quarter) << 16;
     float bad = 0.f;  // max |operand value| seen (fp16 range check)
+    __half2 badh = __floats2half2_rn(0.f, 0.f);  // same for the hidden layers' operands, on packed hi halves
     uint32_t acc_phase = 0;
 
     auto prologue = [&](int64_t tile) {
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             for (int i = 0; i < 8; ++i) tc_hidden_act<ACT>(x[i] + bias, x[i], d1[i]);
             uint32_t h[4], l[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split2(x[2 * i], x[2 * i + 1], h[i], l[i], bad);
+            for (int i = 0; i < 4; ++i) split2h(x[2 * i], x[2 * i + 1], h[i], l[i], badh);
             uint32_t off = (uint32_t)((s0 >> 3) * (kHK * 16) + ch * 16);
             *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                     if (n0 + s0 + i < n_total) save[((size_t)i * 4 + j) * kWidth] = g[i];
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) split2(d1[2 * i] * g[2 * i], d1[2 * i + 1] * g[2 * i + 1], h[i], l[i], bad);
+                for (int i = 0; i < 4; ++i) split2h(d1[2 * i] * g[2 * i], d1[2 * i + 1] * g[2 * i + 1], h[i], l[i], badh);
                 off += 4 * (kHK * 16);
                 *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -550,7 +551,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         if (st.post == 2 && t + 1 < my_tiles) prologue(tile + gridDim.x);
       }
     }
-    if (!(bad < 65504.0f) && P.status) atomicOr(P.status, 4);
+    {
+      const float2 m = __half22float2(badh);
+      if (!(fmaxf(bad, fmaxf(m.x, m.y)) < 65504.0f) && P.status) atomicOr(P.status, 4);
+    }
   }
 
   tc_fence_before();

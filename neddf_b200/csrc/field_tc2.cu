@@ -144,17 +144,6 @@ struct Tc2Params {
 // row of local sample s, type j
 __host__ __device__ __forceinline__ int row_of(int s, int j) { return 64 * (s >> 4) + 16 * j + (s & 15); }
 
-// x = hi + lo with hi, lo fp16; `amax` tracks max |hi| as packed halves (one HMNMX2 per pair: an
-// operand beyond fp16 range rounds to inf and is caught at the end of the kernel)
-__device__ __forceinline__ void split2h(float a, float b, uint32_t& hi, uint32_t& lo, __half2& amax) {
-  __half2 h = __floats2half2_rn(a, b);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
-  amax = __hmax2(amax, __habs2(h));
-}
-
 // write the rows (value, Jx, Jy, Jz) of local sample s at K index k into an operand buffer pair
 __device__ __forceinline__ void store_sample2(unsigned char* hi_buf, unsigned char* lo_buf, int KC, int s, int k,
                                               float v0, float v1, float v2, float v3, __half2& bad, int rows = 4) {

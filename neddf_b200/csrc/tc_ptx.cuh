@@ -262,6 +262,17 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
 }
 
+// same split; the range check on packed halves (one HMNMX2 per pair instead of two FMNMX + FABS: an operand
+// beyond fp16 range rounds to inf and is caught at the end of the kernel)
+__device__ __forceinline__ void split2h(float a, float b, uint32_t& hi, uint32_t& lo, __half2& amax) {
+  __half2 h = __floats2half2_rn(a, b);
+  float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+  amax = __hmax2(amax, __habs2(h));
+}
+
 // write the rows (value, Jx, Jy, Jz) of sample s at K index k into an operand buffer pair;
 // type-major row order: row = 32*j + s.  rows = 4, or 1 when only the value row is consumed.
 __device__ __forceinline__ void store_sample(unsigned char* hi_buf, unsigned char* lo_buf, int KC, int s, int k,
