@@ -31,10 +31,11 @@ def install(patch_trainer: bool = False) -> None:
         except Exception:
             pass
     if patch_trainer:
-        from neddf_b200 import losses, trainer_glue
+        from neddf_b200 import eval_io, losses, trainer_glue
 
         base_trainer = importlib.import_module("neddf.trainer.base_trainer")
         base_trainer.BaseTrainer.construct_ground_truth = trainer_glue.construct_ground_truth
+        base_trainer.BaseTrainer.render_all = eval_io.render_all  # uint8 / PNG / PSNR overlapped with the next frame
         # the loss classes hydra instantiates from config/loss/*.yaml (`_target_: neddf.loss.ColorLoss` ...):
         # same constructors and call signature, one CUDA launch each instead of ~10 element-wise kernels
         ref_loss = importlib.import_module("neddf.loss")

@@ -175,3 +175,54 @@ def test_state_struct_reads_penalty_weights_on_every_call():
     net._packed_key = ("x",)
     net.invalidate()
     assert net._packed_key is None
+
+
+def test_eval_io_writer_matches_the_reference_tail(tmp_path):
+    """eval_io.FrameWriter / render_all keep render_test's arithmetic, file names and frame order
+    (base_trainer.py:146-187); here with CPU tensors and a stub renderer."""
+    import cv2
+    from neddf_b200 import eval_io
+    g = torch.Generator().manual_seed(0)
+    h, w = 20, 24
+
+    class StubRender:
+        def __init__(self):
+            self.iter = None
+
+        def set_iter(self, it):
+            self.iter = it
+
+        def render_image(self, width, height, camera, target_types, downsampling, chunk):
+            assert (width, height, list(target_types), downsampling, chunk) == (w, h, ["color", "depth"], 1, 7)
+            return {"color": torch.rand(h, w, 3, generator=g) * 1.2 - 0.1, "depth": torch.rand(h, w, 1, generator=g) * 5 + 1.5}
+
+    class Cam:
+        def __init__(self):
+            self.updated = 0
+
+        def update_transform(self):
+            self.updated += 1
+
+    class StubTrainer:
+        pass
+
+    tr = StubTrainer()
+    tr.neural_render, tr.chunk = StubRender(), 7
+    tr.dataset = [{"rgb_images": (torch.rand(h, w, 3, generator=g) * 255).numpy()} for _ in range(3)]
+    tr.cameras = [Cam() for _ in range(3)]
+    eval_io.render_all(tr, tmp_path)
+    assert tr.neural_render.iter == -1 and all(c.updated == 1 for c in tr.cameras)
+    # replay the same random stream through the reference's expressions
+    g = torch.Generator().manual_seed(0)
+    gts = [(torch.rand(h, w, 3, generator=g) * 255).numpy().astype(np.uint8) for _ in range(3)]  # the dataset came first
+    frames = []
+    for _ in range(3):
+        frames.append((torch.rand(h, w, 3, generator=g) * 1.2 - 0.1, torch.rand(h, w, 1, generator=g) * 5 + 1.5))
+    for i, (col, dep) in enumerate(frames):
+        rgb_ref = torch.clamp(col * 255, 0, 255).numpy().astype(np.uint8)
+        dep_ref = torch.clamp((dep - 2.0) / 4.0 * 50000 / 256, 0, 255).numpy().astype(np.uint8)
+        assert np.array_equal(cv2.imread(str(tmp_path / f"{i:03}_rgb.png")), rgb_ref)
+        assert np.array_equal(cv2.imread(str(tmp_path / f"{i:03}_depth.png"), cv2.IMREAD_UNCHANGED), dep_ref[:, :, 0])
+        assert np.array_equal(cv2.imread(str(tmp_path / f"{i:03}_rgb_gt.png")), gts[i])
+        mse = np.mean((rgb_ref.astype(np.float64) - gts[i].astype(np.float64)) ** 2)
+        assert abs(eval_io.psnr_uint8(rgb_ref, gts[i]) - 10 * np.log10(255.0 ** 2 / mse)) < 1e-12
