@@ -293,17 +293,19 @@ int32_t neddf_composite_backward(const float* d_dists, const float* d_density, c
                                  const float* g_penalty, float* d_grad_density, float* d_grad_color,
                                  float* d_grad_penalty, void* stream);
 
-/* BaseNeuralRender.sample_pdf with cat_coarse=True (base_neural_render.py:27-115).
+/* BaseNeuralRender.sample_pdf (base_neural_render.py:27-115).
  * in : dists[n_rays,n_edges], weights[n_rays,n_edges-1] (IN/OUT: negative and NaN entries are
  *      zeroed in place exactly as the reference does to its argument, :52-55), u[n_rays,n_new]
- * out: dists_fine[n_rays, n_edges+n_new] sorted; optional ids[n_rays,n_new] (int64,
+ * cat_coarse != 0 (what render_rays uses): out dists_fine[n_rays, n_edges+n_new] = sort(new | coarse edges);
+ * cat_coarse == 0: neighbour-max smoothing of the biased weights (:61-68), out dists_fine[n_rays, n_new].
+ * out: dists_fine sorted; optional ids[n_rays,n_new] (int64,
  *      searchsorted right=True) and cdf[n_rays,n_edges].  The batch-wide NaN fallback
  *      (base_neural_render.py:105-114) is applied on device, per launch like the reference:
  *      d_status (optional) points to TWO int32 - [0] persistent flags (bit1 = "pdf sampling failed"
  *      happened since the host last cleared it), [1] scratch holding this launch's decision. */
 int32_t neddf_sample_pdf(const float* d_dists, float* d_weights, const float* d_u,
-                         int64_t n_rays, int32_t n_edges, int32_t n_new, float* d_dists_fine,
-                         int64_t* d_ids, float* d_cdf, int32_t* d_status, void* stream);
+                         int64_t n_rays, int32_t n_edges, int32_t n_new, int32_t cat_coarse,
+                         float* d_dists_fine, int64_t* d_ids, float* d_cdf, int32_t* d_status, void* stream);
 
 /* The inverse-CDF step alone on a caller-supplied cdf (base_neural_render.py:77-98); used to
  * check sample indices bit-exactly against torch.searchsorted. */

@@ -82,7 +82,7 @@ _SIGNATURES = {
                                             _P, _P, _P, _P]),
     "neddf_composite": (_I32, [_P, _P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P, _P]),
     "neddf_composite_backward": (_I32, [_P, _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "neddf_sample_pdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
+    "neddf_sample_pdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "neddf_invert_cdf": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "neddf_tc_mma_bench": (_I32, [_I32, _I32, _I32, _I32, _I32, _P, _P]),
     "neddf_tc_selftest_ts": (_I32, [_P, _P, _I32, _P, _P, _I32, _P]),

@@ -1,7 +1,8 @@
 // K4: hierarchical (inverse-CDF) resampling, one warp per ray.
 //
-// Reference: BaseNeuralRender.sample_pdf with cat_coarse=True
-// (neddf/render/base_neural_render.py:27-115).
+// Reference: BaseNeuralRender.sample_pdf (neddf/render/base_neural_render.py:27-115), both modes:
+// cat_coarse=True (what render_rays uses: new samples merged with the coarse edges) and cat_coarse=False
+// (neighbour-max smoothing of the weights, :61-68, and only the new samples are returned).
 //
 // Per ray: sanitise + bias the coarse weights, L1-normalise, cumulative sum (fp64 accumulate,
 // fp32 outputs -- torch's CPU cumsum accumulates float in double), binary search
@@ -41,7 +42,7 @@ __device__ __forceinline__ float invert_one(const float* __restrict__ cdf, const
 // smem per warp: cdf[n_edges] | dists[n_edges] | merged[p2]
 __global__ void __launch_bounds__(kPdfWarps * 32)
 sample_pdf_kernel(const float* __restrict__ dists, float* __restrict__ weights, const float* __restrict__ u,
-                  int64_t n_rays, int n_edges, int n_new, int p2, float* __restrict__ dists_fine,
+                  int64_t n_rays, int n_edges, int n_new, int p2, int cat_coarse, float* __restrict__ dists_fine,
                   int64_t* __restrict__ ids_out, float* __restrict__ cdf_out, int* __restrict__ status) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
@@ -50,7 +51,7 @@ sample_pdf_kernel(const float* __restrict__ dists, float* __restrict__ weights, 
   float* s_dist = s_cdf + n_edges;
   float* s_merge = s_dist + n_edges;
   const int n_w = n_edges - 1;
-  const int n_out = n_edges + n_new;
+  const int n_out = cat_coarse ? n_edges + n_new : n_new;
   bool saw_nan = false;
 
   const int64_t n_warps = (int64_t)gridDim.x * kPdfWarps;
@@ -67,7 +68,20 @@ sample_pdf_kernel(const float* __restrict__ dists, float* __restrict__ weights, 
       if (touched) wrow[j] = w;
       w = w + 1e-2f;
       s_merge[j] = w;  // staging for the scan
-      part += (double)fabsf(w);
+      if (cat_coarse) part += (double)fabsf(w);
+    }
+    if (!cat_coarse) {  // :61-68: interior weights <- 0.5 (max(w[j+1], w[j]) + max(w[j-1], w[j])), from the biased weights
+      __syncwarp();
+      for (int j = lane; j < n_w; j += 32) {
+        float w = s_merge[j];
+        if (j >= 1 && j + 1 < n_w) w = NM(0.5f, NA(fmaxf(s_merge[j + 1], w), fmaxf(s_merge[j - 1], w)));
+        s_cdf[j] = w;
+      }
+      __syncwarp();
+      for (int j = lane; j < n_w; j += 32) {
+        s_merge[j] = s_cdf[j];
+        part += (double)fabsf(s_cdf[j]);
+      }
     }
     for (int j = lane; j < n_edges; j += 32) s_dist[j] = drow[j];
 #pragma unroll
@@ -100,11 +114,13 @@ sample_pdf_kernel(const float* __restrict__ dists, float* __restrict__ weights, 
       s_merge[i] = smp;
       saw_nan |= (smp != smp);
     }
-    // ---- cat([samples, dists]) (:102), pad to a power of two with +inf
-    for (int j = lane; j < n_edges; j += 32) {
-      float d = s_dist[j];
-      s_merge[n_new + j] = d;
-      saw_nan |= (d != d);
+    // ---- cat([samples, dists]) (:102) or the samples alone (:104), pad to a power of two with +inf
+    if (cat_coarse) {
+      for (int j = lane; j < n_edges; j += 32) {
+        float d = s_dist[j];
+        s_merge[n_new + j] = d;
+        saw_nan |= (d != d);
+      }
     }
     for (int j = n_out + lane; j < p2; j += 32) s_merge[j] = __int_as_float(0x7f800000);
     __syncwarp();
@@ -160,15 +176,18 @@ __global__ void invert_cdf_kernel(const float* __restrict__ dists, const float* 
 using namespace neddf;
 
 extern "C" int32_t neddf_sample_pdf(const float* d_dists, float* d_weights, const float* d_u, int64_t n_rays,
-                                    int32_t n_edges, int32_t n_new, float* d_dists_fine, int64_t* d_ids,
-                                    float* d_cdf, int32_t* d_status, void* stream) {
+                                    int32_t n_edges, int32_t n_new, int32_t cat_coarse, float* d_dists_fine,
+                                    int64_t* d_ids, float* d_cdf, int32_t* d_status, void* stream) {
   if (n_rays < 0 || n_edges < 2 || n_new < 0) return fail(NEDDF_E_INVALID, "neddf_sample_pdf: bad sizes");
   if (n_rays == 0) return NEDDF_OK;
   if (!d_dists || !d_weights || (!d_u && n_new > 0) || !d_dists_fine)
     return fail(NEDDF_E_INVALID, "neddf_sample_pdf: null device pointer");
-  int n_out = n_edges + n_new;
+  int n_out = cat_coarse ? n_edges + n_new : n_new;
+  if (n_out < 1) return fail(NEDDF_E_INVALID, "neddf_sample_pdf: nothing to produce");
   int p2 = 2;
   while (p2 < n_out) p2 <<= 1;
+  if (p2 < n_edges) p2 = n_edges;  // the merge buffer also stages the weights
+  { int q = 2; while (q < p2) q <<= 1; p2 = q; }
   size_t smem = (size_t)kPdfWarps * (2 * n_edges + p2) * sizeof(float);
   if (smem > 200 * 1024) return fail(NEDDF_E_UNSUPPORTED, "neddf_sample_pdf: too many samples per ray for shared memory");
   cudaStream_t s = (cudaStream_t)stream;
@@ -179,7 +198,7 @@ extern "C" int32_t neddf_sample_pdf(const float* d_dists, float* d_weights, cons
   if (blocks > cap) blocks = cap;
   if (d_status) NEDDF_CUDA_CHECK(cudaMemsetAsync(d_status + 1, 0, sizeof(int32_t), s));
   sample_pdf_kernel<<<(unsigned)blocks, kPdfWarps * 32, smem, s>>>(d_dists, d_weights, d_u, n_rays, n_edges, n_new,
-                                                                   p2, d_dists_fine, d_ids, d_cdf, d_status);
+                                                                   p2, cat_coarse ? 1 : 0, d_dists_fine, d_ids, d_cdf, d_status);
   NEDDF_LAUNCH_CHECK();
   if (d_status) {
     pdf_nan_fallback_kernel<<<sm_count(), 256, 0, s>>>(d_status, d_dists, n_edges, n_rays * (int64_t)n_out, n_out,

@@ -135,11 +135,8 @@ class BaseNeuralRender(nn.Module):
     # ---- a17 ---------------------------------------------------------------------------
     def sample_pdf(self, dists: Tensor, weights: Tensor, samples_fine: int, cat_coarse: bool = True,
                    uniform_rands: Optional[Tensor] = None, return_ids: bool = False):
-        """Hierarchical resampling (base_neural_render.py:27-115).  ``weights`` is sanitised in
-        place like the reference's argument.  Only ``cat_coarse=True`` (the mode render_rays
-        uses) is built."""
-        if not cat_coarse:
-            raise NotImplementedError("neddf_b200: sample_pdf(cat_coarse=False) is not on the render_rays path")
+        """Hierarchical resampling (base_neural_render.py:27-115), both modes.  ``weights`` is sanitised in
+        place like the reference's argument."""
         dists = L.require_cuda_f32(dists, "dists")
         if weights.dtype != torch.float32 or not weights.is_contiguous() or not weights.is_cuda:
             raise RuntimeError("neddf_b200: `weights` must be a contiguous fp32 CUDA tensor (it is updated in place)")
@@ -152,11 +149,11 @@ class BaseNeuralRender(nn.Module):
         u = L.require_cuda_f32(uniform_rands, "uniform_rands")
         if u.shape != (B, samples_fine):
             raise ValueError("uniform_rands must be [batch, samples_fine]")
-        out = torch.empty(B, E + samples_fine, device=device, dtype=torch.float32)
+        out = torch.empty(B, (E if cat_coarse else 0) + samples_fine, device=device, dtype=torch.float32)
         ids = torch.empty(B, samples_fine, device=device, dtype=torch.int64) if return_ids else None
         status = self._status(device)
         with torch.cuda.device(device):
-            L.check(L.lib().neddf_sample_pdf(L.ptr(dists), L.ptr(weights), L.ptr(u), B, E, samples_fine, L.ptr(out),
+            L.check(L.lib().neddf_sample_pdf(L.ptr(dists), L.ptr(weights), L.ptr(u), B, E, samples_fine, 1 if cat_coarse else 0, L.ptr(out),
                                              L.ptr(ids), None, L.ptr(status), L.stream_ptr(device)), "sample_pdf")
         return (out, ids) if return_ids else out
 
@@ -259,7 +256,7 @@ class NeRFRender(BaseNeuralRender):
         # nan asserts cost a device sync; the reference pays four per render_rays call
         self.check_nan = True
         # rays per internal launch in render_image (bounds the [rays, samples] work buffers)
-        self.image_chunk = 65536
+        self.image_chunk = 163840  # 0.76 GB of work buffers; a rank's 80,000- or 160,000-ray shard is one launch sequence
         # Early ray termination (BASELINE.json configs[4]; NOT in the reference, so opt-in): in no-grad image
         # renders the fine pass runs in `termination_segments` depth segments and a ray stops being evaluated
         # once its transmittance falls to `transmittance_eps`.  0.0 = off = the reference's behaviour, bit for

@@ -480,9 +480,14 @@ def sanitise_weights(weights: Tensor) -> Tensor:
     return torch.where(torch.isnan(w), torch.zeros_like(w), w)
 
 
-def pdf_cdf(weights: Tensor) -> Tensor:
-    """Sanitise, +1e-2, L1-normalise, cumsum with leading 0 (base_neural_render.py:52-72)."""
+def pdf_cdf(weights: Tensor, smooth: bool = False) -> Tensor:
+    """Sanitise, +1e-2, [neighbour-max smoothing when not cat_coarse, :61-68], L1-normalise, cumsum with
+    leading 0 (base_neural_render.py:52-72)."""
     w = sanitise_weights(weights) + 1e-2
+    if smooth:
+        w1 = torch.maximum(w[:, 2:], w[:, 1:-1])
+        w2 = torch.maximum(w[:, :-2], w[:, 1:-1])
+        w = torch.cat([w[:, :1], 0.5 * (w1 + w2), w[:, -1:]], -1)
     pdf = torch.nn.functional.normalize(w, p=1.0, dim=-1)
     cdf = torch.cumsum(pdf, -1)
     return torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
@@ -501,12 +506,13 @@ def invert_cdf(dists: Tensor, cdf: Tensor, u: Tensor) -> Tuple[Tensor, Tensor]:
     return d0 + t * (d1 - d0), ids
 
 
-def sample_pdf(dists: Tensor, weights: Tensor, u: Tensor) -> Tensor:
-    """Hierarchical resampling with the coarse edges merged in, cat_coarse=True
-    (neddf/render/base_neural_render.py:27-115).  ``u`` replaces the internal torch.rand."""
-    cdf = pdf_cdf(weights)
+def sample_pdf(dists: Tensor, weights: Tensor, u: Tensor, cat_coarse: bool = True) -> Tensor:
+    """Hierarchical resampling (neddf/render/base_neural_render.py:27-115): with the coarse edges merged in
+    (cat_coarse=True, what render_rays uses) or the new samples alone after the neighbour-max smoothing of the
+    biased weights (:61-68).  ``u`` replaces the internal torch.rand."""
+    cdf = pdf_cdf(weights, smooth=not cat_coarse)
     new, _ = invert_cdf(dists, cdf, u)
-    merged = torch.sort(torch.cat([new, dists], -1), dim=-1)[0]
+    merged = torch.sort(torch.cat([new, dists], -1) if cat_coarse else new, dim=-1)[0]
     if torch.any(torch.isnan(merged)):  # base_neural_render.py:105-114
         merged = torch.linspace(float(dists[0, 0]), float(dists[0, -1]), merged.shape[1],
                                 dtype=dists.dtype).reshape(1, -1).expand(dists.shape[0], -1)

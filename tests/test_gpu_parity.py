@@ -811,3 +811,23 @@ def test_fused_adam_matches_torch_adam_and_repacks():
         b = renders[1].render_rays(uv, cam, uniforms=u)
     for k in ("color", "depth", "fields_penalty"):
         assert nerr(b[k].cpu().numpy(), a[k].cpu().numpy()) < 1e-5, k
+
+
+def test_sample_pdf_without_coarse_edges():
+    """sample_pdf(cat_coarse=False) (base_neural_render.py:61-68, 104) against the real reference's golden
+    output and the oracle; in-place sanitising of the weights as in the other mode."""
+    G = _gpu()
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "case_pdf_nocat.npz"))
+    c = Case("bunny")
+    render = G.build_render(c)
+    wd = torch.from_numpy(z["weights"]).clone().to(G.DEV)
+    out = render.sample_pdf(torch.from_numpy(z["dists"]).to(G.DEV), wd, z["u"].shape[1], cat_coarse=False,
+                            uniform_rands=torch.from_numpy(z["u"]).to(G.DEV))
+    assert out.shape == z["out"].shape
+    assert nerr(out.cpu().numpy(), z["out"]) < 5e-6
+    assert np.array_equal(wd.cpu().numpy(), z["weights_after"], equal_nan=True)
+    o = out.cpu()
+    assert bool((o[:, 1:] >= o[:, :-1]).all())
+    render._status_buf.zero_()
