@@ -606,11 +606,22 @@ def main():
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
-    traffic = None
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture; only valid for the
+    # kernel source it was taken from (hash of field_tc.cu + tc_ptx.cuh) and the engine it profiled
+    traffic, traffic_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "field_kernel_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
+        import hashlib
+        tj = json.load(open(os.path.join(ROOT, "profiles", "field_kernel_traffic.json")))
+        h = hashlib.sha256(b"".join(open(os.path.join(ROOT, f), "rb").read() for f in tj["source_files"])).hexdigest()
+        if h != tj["source_sha256"]:
+            traffic_note = "profiles/field_kernel_traffic.json was captured from a different kernel source - re-run the ncu capture"
+        elif render.network_fine.resolved_engine(dev) != "tc":
+            traffic_note = "the committed capture is of the tc engine"
+        else:
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_note = tj["launch"]
+    except Exception as e:  # noqa: BLE001
+        traffic_note = f"no capture available ({e})"
 
     # end to end through the public API with host buffers
     for _ in range(2):
@@ -620,6 +631,21 @@ def main():
     e2e_value = rays_per_step * NOMINAL_PER_RAY / (ms_e2e * 1e-3)
     h2d = n_frames * count * (S_COARSE + 1 + S_FINE + 1) * 4 + n_frames * 16 * 4
     d2h = n_frames * n_pix * 4 * 4 if rank == 0 else 0
+
+    # strong scaling: ONE frame ray-sharded over the N ranks (latency of a frame), device-resident uniforms
+    strong = None
+    if world > 1:
+        from neddf_b200.dist import gather_tiles
+
+        def one_frame():
+            flat = render.render_pixels(W, H, cams[0], targets, 1, first, count, dev_u[0])
+            return gather_tiles(torch.cat([flat["color"], flat["depth"]], 1), n_pix)
+
+        one_frame()
+        ms_frame, _ = timed(one_frame, max(3, args.steps))
+        ms_frame /= max(3, args.steps)
+        strong = {"frame_ms": ms_frame, "ray_samples_per_s": n_pix * NOMINAL_PER_RAY / (ms_frame * 1e-3),
+                  "note": "one 800x800 frame sharded over the ranks + the all-gather of the image tiles"}
 
     cpu, parity = None, None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:  # reported at N=1 only
@@ -641,12 +667,13 @@ def main():
             "data": "synthetic", "config": workload_config(n_gpus, engine),
             "mlp_evaluations_per_s": rays_per_step * EVALS_PER_RAY / (ms_step * 1e-3),
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak if peak else None, "traffic": traffic,
+                         "frac": achieved_tflops / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
                          "kernel": "field megakernel (NeDDF.forward fused)", "peak_source": peak_src,
                          "flop_per_evaluation": flop, "launches_timed": len(evs),
                          "kernel_share_of_step": kms / ms_total if ms_total else None},
             "cpu_baseline": cpu,
             "parity": parity,
+            "strong_scaling": strong,
             "early_termination": None if args.eps <= 0 else {
                 "transmittance_eps": args.eps, "segments": args.segments,
                 "fine_evaluations_executed": term["executed"], "fine_evaluations_nominal": term["nominal"],

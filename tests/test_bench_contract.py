@@ -56,3 +56,13 @@ def test_product_weights_equal_the_oracle_stream(repo_root):
     src = open(os.path.join(repo_root, "bench.py")).read()
     main_src = src[src.index("def main():"):]
     assert "oracle" not in main_src.split("cpu_port_rate")[0]  # product arm set-up imports no oracle
+
+
+def test_committed_traffic_capture_matches_the_kernel_source(repo_root):
+    """roofline.traffic comes from the committed ncu capture; it is only reported for the kernel source it was
+    taken from.  A stale JSON (kernel edited, capture not redone) fails here instead of being silently dropped."""
+    import hashlib
+    tj = json.load(open(os.path.join(repo_root, "profiles", "field_kernel_traffic.json")))
+    h = hashlib.sha256(b"".join(open(os.path.join(repo_root, f), "rb").read() for f in tj["source_files"])).hexdigest()
+    assert h == tj["source_sha256"], "field_tc.cu / tc_ptx.cuh changed: redo the ncu --set full capture and refresh the JSON"
+    assert tj["dram_bytes_per_launch"] == tj["dram_bytes_read"] + tj["dram_bytes_write"]
