@@ -192,13 +192,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
   Scratch* sc = reinterpret_cast<Scratch*>(smem + kOffScratch);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  // Warp index, tile count and the tensor-memory base go through a shuffle so that ptxas can prove them
+  // warp-uniform: the MMA issuer's loop then runs on the uniform datapath (descriptors in uniform registers,
+  // three UTCHMMA back to back) instead of ~17 R2UR moves per chunk under an elected lane.
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lane = tid & 31;
 
   const int64_t n_total = field_total(p);
   const int64_t n_tiles = (n_total + kTileS - 1) / kTileS;
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - blockIdx.x) / gridDim.x + 1;
+  my_tiles = __shfl_sync(0xffffffffu, my_tiles, 0);
   const int64_t total_chunks = my_tiles * P.chunks_per_tile;
 
   if (tid == 0) {
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = sc->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sc->tmem_base, 0);
 
   if (warp > kMmaWarp) {
     // ===================== weight loaders: L2 -> registers -> tensor memory ======================

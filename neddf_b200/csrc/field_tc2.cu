@@ -66,13 +66,23 @@ constexpr int kARing = 8;                             // chunks resident in tens
 #define NEDDF_TC2_TMA_SPLIT 1
 #endif
 constexpr int kTmaSplit = NEDDF_TC2_TMA_SPLIT;          // bulk copies per chunk
-constexpr int kSStages = 2;                           // shared-memory staging ring of the TMA copies
+#ifndef NEDDF_TC2_SSTAGES
+#define NEDDF_TC2_SSTAGES 3
+#endif
+constexpr int kSStages = NEDDF_TC2_SSTAGES;                           // shared-memory staging ring of the TMA copies
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;
 constexpr int kTmaWarp = kEpiWarps + 1;
 constexpr int kCpWarp = kEpiWarps + 2;
-constexpr int kThreads = kEpiThreads + 3 * 32;
+constexpr int kFinWarp = kEpiWarps + 3;  // finishes the heads (density, normals, colour, penalties, outputs)
+#ifndef NEDDF_TC2_CP_ISSUERS
+#define NEDDF_TC2_CP_ISSUERS 1
+#endif
+constexpr int kCpIssuers = NEDDF_TC2_CP_ISSUERS;  // threads (one per warp) that move staged chunks to tensor memory, chunk c by issuer c % kCpIssuers
+constexpr int kCpWarp2 = kEpiWarps + 4;           // the second one
+constexpr int kThreads = kEpiThreads + (3 + kCpIssuers) * 32;
+constexpr int kWsFloats = 8 * kTileS * 12;  // per-CTA global workspace: head partial sums
 constexpr uint32_t kACol = 256;  // first TMEM column of the weight ring
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxSteps = kMaxHidden;
@@ -89,9 +99,6 @@ constexpr uint32_t kOffScratch = kOffStage + kSStages * kWChunkBytes;
 
 struct Scratch {
   float geo[kTileS][12];  // pos[3], dir[3], var[3], pad
-  HeadOut head[kTileS];
-  // head partial sums [contributor = 4 * rank + lane quarter][local sample][3 * row type + output]
-  float hsum[8][kTileS][12];
   uint64_t s_full[kSStages];     // TMA -> (this CTA's) cp issuer / forwarder: chunk landed in shared memory
   uint64_t s_empty[kSStages];    // tcgen05.commit (multicast) -> TMA producers: staged chunk copied to tensor memory
   uint64_t peer_full[kSStages];  // (leader) the peer's chunk landed in the peer's shared memory
@@ -99,14 +106,16 @@ struct Scratch {
   uint64_t a_empty[kARing];      // (leader) tcgen05.commit -> cp issuer: chunk consumed by both passes
   uint64_t act_ready[2];     // (leader) epilogue warps of both CTAs -> MMA: accumulator hs drained, B rows of half hs rewritten
   uint64_t acc_ready[2];     // MMA -> epilogue warps (multicast commit): accumulator hs complete
-  uint64_t head_ready[2];    // partial head sums of this CTA's samples of half hs are in hsum
-  uint64_t norm_ready;       // (leader) both CTAs wrote the surface normals into AUX
+  uint64_t head_ready[2];    // partial head sums of this CTA's samples of half hs are in the workspace (one arrival per CTA)
+  uint64_t norm_ready[2];    // (leader) both CTAs wrote the surface normals of half hs into AUX
+  uint64_t fin_done[2];      // the finishing warps of both CTAs consumed the sums of head type k (0 = distance / aux, 1 = colour)
   long long t_issue[kSStages];  // profiling aid: when the producer issued the copy into each staging slot
   uint32_t tmem_base;
   uint32_t pad;
 };
 constexpr uint32_t kSmemBytes = kOffScratch + sizeof(Scratch);
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kCpIssuers == 1 || kSStages % kCpIssuers == 0, "every copy issuer must see every phase of the staging barriers it waits on");
 
 struct Step {
   int aux_ksteps;  // K-steps (16) taken from AUX
@@ -127,6 +136,7 @@ struct Tc2Params {
   const unsigned char* w;  // packed chunks: [(chunk, rank)] x kWChunkBytes in consumption order
   const float* bias;       // [n_hidden][256]
   const float* w_head;     // [256][8]: ddf, aux, r, g, b, 0, 0, 0
+  float* ws;               // [CTA][contributor = 4 * rank + lane quarter][local sample][3 * row type + output] head partial sums
   int* status;
   int eval;             // 1 = images only
   long long* timeline;  // optional: CTA 0 writes 6 values per step
@@ -314,7 +324,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
   Scratch* sc = reinterpret_cast<Scratch*>(smem + kOffScratch);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  // warp index, tile count and tensor-memory base through a shuffle: provably warp-uniform, so the single-thread
+  // roles (MMA issuer, copy issuers, producer) compile to uniform-datapath code (see field_tc.cu)
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int64_t cid = blockIdx.x >> 1;
@@ -324,6 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
   const int64_t n_tiles = (n_total + kPairS - 1) / kPairS;
   int64_t my_tiles = 0;
   if (cid < n_tiles) my_tiles = (n_tiles - 1 - cid) / n_clusters + 1;
+  my_tiles = __shfl_sync(0xffffffffu, my_tiles, 0);
   const int64_t total_chunks = my_tiles * P.chunks_per_tile;
 
   if (tid == 0) {
@@ -341,7 +354,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
       mbar_init(&sc->acc_ready[h], 1);
       mbar_init(&sc->head_ready[h], 2);             // one arrival per CTA: its partial sums for this CTA's samples are written
     }
-    mbar_init(&sc->norm_ready, 2 * 32);               // every lane of the finishing warp of both CTAs
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&sc->norm_ready[h], 2 * 16);          // the 16 lanes (samples of half h) of the finishing warp of both CTAs
+      mbar_init(&sc->fin_done[h], 2);                 // lane 0 of the finishing warp of both CTAs
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) tmem_alloc2(&sc->tmem_base, kTmemCols);
@@ -349,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem = sc->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, sc->tmem_base, 0);
 
   if (warp == kTmaWarp) {
     // ===================== TMA producer: this CTA's chunks, L2 -> shared-memory staging ring =========
@@ -370,12 +386,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
         if (++idx == P.chunks_per_tile) idx = 0;
       }
     }
-  } else if (warp == kCpWarp) {
+  } else if (warp == kCpWarp || warp == kCpWarp2) {
     if (lane == 0) {
+      const int64_t c_first = (warp == kCpWarp) ? 0 : 1;
       if (rank != 0) {
         // ===================== peer: tell the leader when a chunk has landed here ==================
         const uint32_t pf0 = mapa_u32(smem_u32(&sc->peer_full[0]), 0);
-        for (int64_t c = 0; c < total_chunks; ++c) {
+        for (int64_t c = c_first; c < total_chunks; c += kCpIssuers) {
           const int s = (int)(c % kSStages);
           mbar_wait(&sc->s_full[s], (uint32_t)((c / kSStages) & 1));
           mbar_arrive_cluster_relaxed(pf0 + 8 * s);  // the data stays in this CTA; its tcgen05.cp is ordered by the TMA completion observed here
@@ -383,7 +400,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
       } else {
         // ===================== leader: staged chunks of both CTAs -> tensor-memory ring ============
         const uint32_t st0 = smem_u32(smem + kOffStage);
-        for (int64_t c = 0; c < total_chunks; ++c) {
+        for (int64_t c = c_first; c < total_chunks; c += kCpIssuers) {
           const int s = (int)(c % kSStages), t = (int)(c % kARing);
           const uint32_t ph = (uint32_t)((c / kSStages) & 1);
           const bool cstamp = P.timeline && (P.debug & 128) && blockIdx.x == 0 && (c + 1) * 6 <= P.timeline_cap;
@@ -407,8 +424,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
 #pragma unroll
           for (int u = 0; u < 2 * kChunkK; ++u)
             tmem_cp2_128x256b(ta + 8 * u, make_desc(st0 + s * kWChunkBytes + u * 4096, 128, 256));
+          const long long cm0 = cstamp ? clock64() : 0;
           mma2_commit(smem_u32(&sc->a_full[t]), 1);   // MMA warp: the chunk is in tensor memory (both CTAs)
+          const long long cm1 = cstamp ? clock64() : 0;
           mma2_commit(smem_u32(&sc->s_empty[s]), 3);  // producers of both CTAs: the staging slot is free
+          if (cstamp) P.timeline[6 * c + 5] = ((clock64() - cm1) << 40) | ((cm1 - cm0) << 20) | (cm0 - P.timeline[6 * c + 4]);
         }
       }
     }
@@ -435,7 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
           // two-pass groups of at most NEDDF_TC2_GROUP chunks (the ring holds a whole group)
           const int n_groups = (nT + P.group - 1) / P.group;
           const int g_len = (nT + n_groups - 1) / n_groups;
-          bool norm_waited = !(st.colour && st.aux_ksteps > 0);  // colour layer 0 reads the normals from AUX
+          const bool needs_norm = st.colour && st.aux_ksteps > 0;  // colour layer 0 reads the normals from AUX
           if (stamp) P.timeline[6 * tl + 0] = clock64();
           for (int gb = 0; gb < nT; gb += g_len) {
             const int ge = (gb + g_len < nT) ? gb + g_len : nT;
@@ -455,6 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               stage = stage0;
               full_par = par0;
               uint32_t acc = gb > 0;
+              bool norm_waited = !needs_norm;
               if ((P.debug & 2) && gb == 0) {
                 const long long t0 = clock64();
                 while (clock64() - t0 < 200000) {}
@@ -515,9 +536,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               if (b2 < e2) {
                 if (!part1_aux) {
                   if (!norm_waited) {  // the surface normals (AUX K rows n_e0 + n_d ..) of both CTAs
-                    mbar_wait(&sc->norm_ready, norm_phase);
+                    mbar_wait(&sc->norm_ready[hs], norm_phase);
                     tc_fence_after();
-                    norm_phase ^= 1;
                     norm_waited = true;
                   }
                   run(dba_hi + (b2 - first_n) * (16 * kChunkK), dba_lo + (b2 - first_n) * (16 * kChunkK), e2 - b2);
@@ -529,9 +549,104 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
             }
           }
           act_phase ^= 1;
+          if (needs_norm) norm_phase ^= 1;
           if (stamp) P.timeline[6 * tl + 1] = clock64();
         }
       }
+    }
+  } else if (warp == kFinWarp) {
+    // ===================== finishing warp: heads -> density / normals / colour / penalties / outputs ========
+    // lane = local sample of this CTA; the two sample halves are finished as their sums arrive, so the
+    // normals of half 0 reach AUX while the last trunk layer still works on half 1.
+    const int s = lane, hs_own = lane >> 4;
+    const float* hsum = P.ws + (size_t)blockIdx.x * kWsFloats;  // [contributor][sample][12]
+    const uint32_t norm0 = mapa_u32(smem_u32(&sc->norm_ready[0]), 0);
+    const uint32_t fin_c0 = mapa_u32(smem_u32(&sc->fin_done[0]), 0), fin_c1 = mapa_u32(smem_u32(&sc->fin_done[0]), 1);
+    __half2 bad = __floats2half2_rn(0.f, 0.f);
+    uint32_t head_phase = 0;
+    HeadOut ho;  // of sample `lane`, kept from the distance heads to the colour head
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int64_t tile = cid + t * n_clusters;
+      const int64_t n = tile * kPairS + kTileS * rank + s;
+      // ---- distance / aux heads (neddf.py:212-241), normals into AUX for the colour trunk (:243-253) ----
+      for (int hs = 0; hs < 2; ++hs) {
+        mbar_wait(&sc->head_ready[hs], head_phase);
+        fence_acq_rel_cluster();  // the sums were written by both CTAs (global memory, read from L2)
+        if (hs == hs_own) {
+          float ddf[4] = {0.f, 0.f, 0.f, 0.f}, aux[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4* q = reinterpret_cast<const float4*>(hsum + ((size_t)c * kTileS + s) * 12);
+            const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
+            ddf[0] += q0.x; aux[0] += q0.y;
+            ddf[1] += q0.w; aux[1] += q1.x;
+            ddf[2] += q1.z; aux[2] += q1.w;
+            ddf[3] += q2.y; aux[3] += q2.z;
+          }
+          ddf[0] += __ldg(p.b_head + 0);
+          aux[0] += __ldg(p.b_head + 1);
+          head_density(ddf, aux, p.d_near, p.aux_grad_scale, p.density_act, ho);
+          const int kn = p.n_e0 + p.n_d;  // normal: detached, zero Jacobian
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            store_sample2(aux_hi, aux_lo, kAuxK, s, kn + i, ho.normal[i], 0.f, 0.f, 0.f, bad, P.eval ? 1 : 4);
+          fence_async_all();
+          mbar_arrive_cluster(norm0 + 8 * hs);  // every lane after its own writes
+        }
+      }
+      head_phase ^= 1;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(fin_c0);
+        mbar_arrive_cluster(fin_c1);
+      }
+      // ---- colour head (neddf.py:257) + penalties (:259-300) + outputs ----
+      for (int hs = 0; hs < 2; ++hs) {
+        mbar_wait(&sc->head_ready[hs], head_phase);
+        fence_acq_rel_cluster();
+        if (hs == hs_own) {
+          float col[3] = {0.f, 0.f, 0.f}, colJ[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4* q = reinterpret_cast<const float4*>(hsum + ((size_t)c * kTileS + s) * 12);
+            const float4 q0 = __ldcg(q);
+            col[0] += q0.x; col[1] += q0.y; col[2] += q0.z;
+            if (!P.eval) {
+              const float4 q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
+              colJ[0][0] += q0.w; colJ[0][1] += q1.x; colJ[0][2] += q1.y;
+              colJ[1][0] += q1.z; colJ[1][1] += q1.w; colJ[1][2] += q2.x;
+              colJ[2][0] += q2.y; colJ[2][1] += q2.z; colJ[2][2] += q2.w;
+            }
+          }
+          if (n < n_total) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) col[o] += __ldg(p.b_head + 2 + o);
+            int64_t ray_, on;  // where this sample's outputs go (segment view: [ray, edge] of the full arrays)
+            int j_;
+            field_map(p, n, ray_, j_, on);
+            if (p.distance) p.distance[on] = ho.distance;
+            if (p.density) p.density[on] = ho.density;
+            if (p.aux_grad) p.aux_grad[on] = ho.aux;
+            if (p.color) {
+              p.color[3 * on + 0] = col[0];
+              p.color[3 * on + 1] = col[1];
+              p.color[3 * on + 2] = col[2];
+            }
+            // (in images-only mode the colour Jacobian rows are not computed and no penalty is asked)
+            if (p.penalty) p.penalty[on] = field_penalty(ho, col, colJ, p.distance_range_max, p.penalty_weight);
+          }
+        }
+      }
+      head_phase ^= 1;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(fin_c0 + 8);
+        mbar_arrive_cluster(fin_c1 + 8);
+      }
+    }
+    {
+      const float2 m = __half22float2(bad);
+      if (!(fmaxf(m.x, m.y) < 65504.0f) && P.status) atomicOr(P.status, 4);
     }
   } else {
     // ===================== epilogue warps =====================================================
@@ -546,12 +661,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
     const bool skip_remote = remote && (P.debug & 32);
     // destination operand buffers: own shared memory or the peer's
     const uint32_t dst_hhi = mapa_u32(smem_u32(h_hi), tcta), dst_hlo = mapa_u32(smem_u32(h_lo), tcta);
-    const uint32_t dst_hsum = mapa_u32(smem_u32(&sc->hsum[4 * rank + quarter][0][0]), tcta);
+    // head partial sums of this warp go to the owner of its samples (global workspace, L2)
+    float* dst_hsum = P.ws + ((size_t)(2 * cid + tcta) * 8 + 4 * rank + quarter) * (kTileS * 12);
     const uint32_t act0 = mapa_u32(smem_u32(&sc->act_ready[0]), 0);
-    const uint32_t norm0 = mapa_u32(smem_u32(&sc->norm_ready), 0);
     __half2 bad = __floats2half2_rn(0.f, 0.f);  // max |operand hi part| seen (fp16 range check)
     uint32_t acc_phase = 0;
-    uint32_t head_phase = 0;
+    uint32_t fin_phase[2] = {0, 0};
     // head weights of this thread's channel: ddf, aux, r, g, b
     float wh[5];
     {
@@ -614,7 +729,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
 
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int64_t tile = cid + t * n_clusters;
-      const int64_t n_own = tile * kPairS + kTileS * rank;  // first sample this CTA owns
       for (int si = 0; si < P.n_steps; ++si) {
         const Step& st = P.step[si];
         const float bias = __ldg(P.bias + st.bias_off + ch);
@@ -623,7 +737,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
         const int tl = (int)(t * P.n_steps + si);
         const bool stamp = P.timeline && !(P.debug & (128 | 512)) && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
         for (int hs = 0; hs < 2; ++hs) {
-          if (lane == 0) mbar_wait(&sc->acc_ready[hs], acc_phase);
+          if (lane == 0) {
+            mbar_wait(&sc->acc_ready[hs], acc_phase);
+            // the previous tile's sums of this head type were consumed by the finishing warps of both CTAs
+            if (st.head != 0 && hs == 0 && t > 0) mbar_wait(&sc->fin_done[st.head - 1], fin_phase[st.head - 1]);
+          }
           __syncwarp();
           tc_fence_after();
           if (stamp) P.timeline[6 * tl + 2 + 2 * hs] = clock64();
@@ -685,7 +803,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
               }
               warp_transpose_reduce16(hv, lane);  // lane L: sample L >> 2, output (L >> 1) & 1
               if ((lane & 1) == 0)
-                st_cluster_f32(dst_hsum + (uint32_t)(((s0 + (lane >> 2)) * 12 + 3 * j + ((lane >> 1) & 1)) * 4), hv[0]);
+                __stcg(dst_hsum + (s0 + (lane >> 2)) * 12 + 3 * j + ((lane >> 1) & 1), hv[0]);
             } else if (st.head == 2) {
               float hv[32];
 #pragma unroll
@@ -696,7 +814,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
                 hv[4 * i + 3] = 0.f;
               }
               warp_transpose_reduce<32>(hv, lane);  // lane L: sample L >> 2, output L & 3
-              if ((lane & 3) != 3) st_cluster_f32(dst_hsum + (uint32_t)(((s0 + (lane >> 2)) * 12 + 3 * j + (lane & 3)) * 4), hv[0]);
+              if ((lane & 3) != 3) __stcg(dst_hsum + (s0 + (lane >> 2)) * 12 + 3 * j + (lane & 3), hv[0]);
             }
           };
           head_rows(x, 0);
@@ -739,68 +857,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) field_t
         // shared-memory writes are published by the fence + arrive of the following steps
         if (st.post == 1) colour_prep();
         if (st.post == 2 && t + 1 < my_tiles) prologue(tile + n_clusters);
-        if (st.head != 0 && warp == 0) {
-          // ---- one warp finishes the heads for the 32 samples this CTA owns (lane = sample) ----
-          mbar_wait(&sc->head_ready[0], head_phase);
-          mbar_wait(&sc->head_ready[1], head_phase);
-          head_phase ^= 1;
-          const int s = lane;
-          if (st.head == 1) {
-            float ddf[4] = {0.f, 0.f, 0.f, 0.f}, aux[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                ddf[j] += sc->hsum[c][s][3 * j + 0];
-                aux[j] += sc->hsum[c][s][3 * j + 1];
-              }
-            }
-            ddf[0] += __ldg(p.b_head + 0);
-            aux[0] += __ldg(p.b_head + 1);
-            HeadOut ho;
-            head_density(ddf, aux, p.d_near, p.aux_grad_scale, p.density_act, ho);
-            sc->head[s] = ho;
-            const int kn = p.n_e0 + p.n_d;  // normal: detached, zero Jacobian (neddf.py:243-253)
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-              store_sample2(aux_hi, aux_lo, kAuxK, s, kn + i, ho.normal[i], 0.f, 0.f, 0.f, bad, P.eval ? 1 : 4);
-            fence_async_all();
-            mbar_arrive_cluster(norm0);  // every lane after its own writes
-          } else {
-            // colour head (neddf.py:257) + penalties (:259-300) + outputs
-            const int64_t n = n_own + s;
-            float col[3] = {0.f, 0.f, 0.f}, colJ[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-#pragma unroll
-              for (int o = 0; o < 3; ++o) {
-                col[o] += sc->hsum[c][s][o];
-                if (!P.eval) {
-#pragma unroll
-                  for (int i = 0; i < 3; ++i) colJ[i][o] += sc->hsum[c][s][3 * (1 + i) + o];
-                }
-              }
-            }
-            if (n < n_total) {
-              const HeadOut& ho = sc->head[s];
-#pragma unroll
-              for (int o = 0; o < 3; ++o) col[o] += __ldg(p.b_head + 2 + o);
-              int64_t ray_, on;  // where this sample's outputs go (segment view: [ray, edge] of the full arrays)
-              int j_;
-              field_map(p, n, ray_, j_, on);
-              if (p.distance) p.distance[on] = ho.distance;
-              if (p.density) p.density[on] = ho.density;
-              if (p.aux_grad) p.aux_grad[on] = ho.aux;
-              if (p.color) {
-                p.color[3 * on + 0] = col[0];
-                p.color[3 * on + 1] = col[1];
-                p.color[3 * on + 2] = col[2];
-              }
-              // (in images-only mode the colour Jacobian rows are not computed and no penalty is asked)
-              if (p.penalty) p.penalty[on] = field_penalty(ho, col, colJ, p.distance_range_max, p.penalty_weight);
-            }
-          }
-        }
+        if (st.head != 0 && t > 0) fin_phase[st.head - 1] ^= 1;
       }
     }
     {
@@ -874,6 +931,7 @@ struct Storage {
   float* d_bias = nullptr;
   float* d_w_head = nullptr;
   int* d_status = nullptr;
+  float* d_ws = nullptr;  // head partial sums, one block per CTA of the largest grid
   int n_steps = 0;
   int chunks_per_tile = 0;
   Step step[kMaxSteps];
@@ -942,12 +1000,14 @@ static int32_t tc2_ensure(neddf_field* f) {
   if (cudaMalloc(&S->d_w, (size_t)chunk * 2 * tc2::kWChunkBytes) != cudaSuccess ||
       cudaMalloc(&S->d_bias, (size_t)n_hidden * kWidth * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&S->d_w_head, (size_t)kWidth * 8 * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess) {
-    cudaFree(S->d_w); cudaFree(S->d_bias); cudaFree(S->d_w_head); cudaFree(S->d_status);
+      cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&S->d_ws, (size_t)sm_count() * tc2::kWsFloats * sizeof(float)) != cudaSuccess) {
+    cudaFree(S->d_w); cudaFree(S->d_bias); cudaFree(S->d_w_head); cudaFree(S->d_status); cudaFree(S->d_ws);
     delete S;
     return fail(NEDDF_E_CUDA, "tensor-core pair engine: cudaMalloc failed");
   }
   cudaMemset(S->d_status, 0, sizeof(int));
+  cudaMemset(S->d_ws, 0, (size_t)sm_count() * tc2::kWsFloats * sizeof(float));
   f->tc2 = S;
   return NEDDF_OK;
 }
@@ -959,6 +1019,7 @@ void tc2_destroy(neddf_field* f) {
   cudaFree(S->d_bias);
   cudaFree(S->d_w_head);
   cudaFree(S->d_status);
+  cudaFree(S->d_ws);
   delete S;
   f->tc2 = nullptr;
 }
@@ -992,6 +1053,7 @@ int32_t launch_field_tc2(const neddf_field* f, FieldParams& p, int flags, cudaSt
   P.bias = S->d_bias;
   P.w_head = S->d_w_head;
   P.status = S->d_status;
+  P.ws = S->d_ws;
   P.eval = (flags == NEDDF_OUT_EVAL && p.penalty == nullptr && p.save_pre == nullptr) ? 1 : 0;
   P.timeline = S->timeline;
   P.timeline_cap = S->timeline_cap;

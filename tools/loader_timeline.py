@@ -26,5 +26,6 @@ t = buf.cpu().view(-1, 6)
 t = t[t[:, 0] != 0]
 print("chunk  wait_start->landed  tma_latency(issue->landed)  peer_extra  stage_free_extra  period")
 for i in range(158, min(len(t), 158 + 79)):
-    a, ti, b, c, d, _ = [int(x) for x in t[i]]
-    print(f"{i:5d} {b - a:12d} {b - ti:18d} {c - b:14d} {d - c:14d} {a - int(t[i - 1][0]):10d}")
+    a, ti, b, c, d, e = [int(x) for x in t[i]]
+    print(f"{i:5d} {b - a:12d} {b - ti:18d} {c - b:14d} {d - c:14d} {a - int(t[i - 1][0]):10d}"
+          f"   cp x4 {e & 0xfffff:5d}  commit a_full {(e >> 20) & 0xfffff:5d}  commit s_empty {e >> 40:5d}")

@@ -11,7 +11,7 @@ R, T, calib = bench.synthetic_pose(0)
 cam = neddf_b200.Camera.from_matrix(neddf_b200.PinholeCalib(calib), R, T).to(dev); cam.update_transform()
 first = (bench.H // 2) * bench.W
 render = neddf_b200.NeRFRender(network_config=bench.NET_CFG, **bench.RENDER_CFG)
-render.load_state_dict(sd); render.to(dev); render.set_iter(-1); render.set_engine("tc2"); render.check_nan = False
+render.load_state_dict(sd); render.to(dev); render.set_iter(-1); render.set_engine(os.environ.get("ENGINE", "tc2")); render.check_nan = False
 n_rays = 65536
 render.render_pixels(bench.W, bench.H, cam, ["color", "depth"], 1, first, n_rays)
 groups = [int(g) for g in os.environ.get("TC2_GROUPS", "8").split(",")]
