@@ -118,7 +118,19 @@ struct TcParams {
                         // 4 = loaders skip the TMEM stores, 8 = epilogue skips the hidden-layer math; results are garbage
   long long* timeline;  // optional: CTA 0 writes 6 values per step (profiling aid)
   int timeline_cap;
+  // Batched colour trunk (images only): `batch` tiles run the distance trunk one after the other, park the value
+  // rows of their features and colour inputs in `stash`, then ONE pass of the colour trunk serves all of them as
+  // the 128 rows of the operand (row = 32 slot + sample): the colour weights are streamed once per 128 samples
+  // and its MMAs are N = 128 instead of N = 32.  batch == 1 is the per-tile program.
+  int batch;
+  int n_trunk;        // steps of the distance trunk incl. its heads (= head_da_step + 1)
+  int chunks_trunk;   // weight chunks of those steps (the colour trunk's follow in the packed stream)
+  unsigned char* stash;  // [CTA][slot][H hi 16 KB | H lo 16 KB | AUX hi 6 KB | AUX lo 6 KB] value rows in operand layout
 };
+constexpr uint32_t kStashH = 4 * kHK * 16;      // four row groups (32 value rows) of H: 16 KB
+constexpr uint32_t kStashAux = 4 * kAuxK * 16;  // of AUX: 6 KB
+constexpr uint32_t kStashSlot = 2 * kStashH + 2 * kStashAux;
+constexpr int kMaxBatch = kRows / kTileS;       // 4 slots
 
 // ---------------------------------------------------------------------------------------------
 // prologue pieces (epilogue warps)
@@ -203,7 +215,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - 1 - blockIdx.x) / gridDim.x + 1;
   my_tiles = __shfl_sync(0xffffffffu, my_tiles, 0);
-  const int64_t total_chunks = my_tiles * P.chunks_per_tile;
+  const int chunks_colour = P.chunks_per_tile - P.chunks_trunk;
+  const int64_t n_groups = (my_tiles + P.batch - 1) / P.batch;
+  const int64_t total_chunks = my_tiles * P.chunks_trunk + n_groups * chunks_colour;
 
   if (tid == 0) {
     for (int i = 0; i < kARing; ++i) {
@@ -246,26 +260,45 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
       for (int j = 0; j < 4; ++j) r[slot][j] = __ldg(src + j);
     };
-    // chunks_per_tile is even, so the within-tile index of chunk g has the parity of g
-    int fidx = cpar;  // within-tile index of the next chunk to fetch
-    int64_t gf = cpar;
+    // Consumption order: per group of `batch` tiles the trunk chunks [0, chunks_trunk) once per tile, then the
+    // colour chunks [chunks_trunk, chunks_per_tile) once.  Both counts are even, so the index of chunk g within
+    // the packed stream has the parity of g.
+    // (32-bit counters: a CTA's share of a launch is far below 2^31 chunks, and the loader warps have no register to spare)
+    const int total = (int)total_chunks;
+    int fidx = cpar;  // index (in the packed stream) of the next chunk to fetch
+    int gf = cpar;
+    int f_ti = 0;                  // tile of the group being fetched
+    int f_left = (int)my_tiles;    // tiles not yet begun, incl. this group
+    int f_ng = f_left < P.batch ? f_left : P.batch;
+    auto advance = [&]() {
+      fidx += kLoadPerQuarter;
+      gf += kLoadPerQuarter;
+      if (f_ti < f_ng) {              // in the trunk stream of tile f_ti
+        if (fidx >= P.chunks_trunk) {
+          if (++f_ti < f_ng) fidx -= P.chunks_trunk;  // next tile of the group; else run on into the colour chunks
+        }
+      } else if (fidx >= P.chunks_per_tile) {  // colour stream done: next group
+        fidx -= P.chunks_per_tile;
+        f_left -= f_ng;
+        f_ng = f_left < P.batch ? f_left : P.batch;
+        f_ti = 0;
+      }
+    };
 #pragma unroll
     for (int i = 0; i < kDepth; ++i) {
-      if (gf < total_chunks) {
+      if (gf < total) {
         fetch(i, fidx);
-        fidx += kLoadPerQuarter;
-        if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
-        gf += kLoadPerQuarter;
+        advance();
       }
     }
     int stage = cpar;
     uint32_t par = 0;
     bool first_pass = true;
-    int64_t g = cpar;
-    while (g < total_chunks) {
+    int g = cpar;
+    while (g < total) {
 #pragma unroll
       for (int i = 0; i < kDepth; ++i) {
-        if (g < total_chunks) {
+        if (g < total) {
           if (!first_pass) mbar_wait(&sc->a_empty[stage], par);
           tc_fence_after();
           const uint32_t ta = tmem + lane_addr + kACol + stage * 16;
@@ -274,11 +307,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           if (!(P.debug & 4)) {
             tmem_st16(ta, w0, w1);  // 8 hi words | 8 lo words of this lane's row
           }
-          if (gf < total_chunks && !(P.debug & 2)) {  // refill this register slot (the scoreboard orders it after the stores read it)
-            fetch(i, fidx);
-            fidx += kLoadPerQuarter;
-            if (fidx >= P.chunks_per_tile) fidx -= P.chunks_per_tile;
-            gf += kLoadPerQuarter;
+          if (gf < total) {  // refill this register slot (the scoreboard orders it after the stores read it)
+            if (!(P.debug & 2)) fetch(i, fidx);
+            advance();
           }
           tmem_st_wait();
           tc_fence_before();
@@ -300,15 +331,21 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     int stage = 0;          // ring position of the next chunk
     uint32_t full_par = 0;  // parity to wait for on a_full[stage]
     uint32_t act_phase = 0;
-    for (int64_t t = 0; t < my_tiles; ++t) {
-      for (int si = 0; si < P.n_steps; ++si) {
+    const bool batched = P.batch > 1;
+    int tl = 0;  // step instance counter (profiling stamps)
+    // program: per group of `batch` tiles the trunk steps [0, n_trunk) of every tile, then the colour steps once
+    for (int64_t t0 = 0; t0 < my_tiles; t0 += P.batch) {
+      const int ng = (int)((my_tiles - t0 < P.batch) ? my_tiles - t0 : P.batch);
+      for (int ti = 0; ti <= ng; ++ti) {  // ti == ng: the colour steps
+      const int si_begin = ti < ng ? 0 : P.n_trunk, si_end = ti < ng ? P.n_trunk : P.n_steps;
+      for (int si = si_begin; si < si_end; ++si, ++tl) {
         const Step& st = P.step[si];
-        const int tl = (int)(t * P.n_steps + si);
         const bool stamp = P.timeline && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
         // act_ready[h] of the previous step: epilogue group h has drained accumulator h and
-        // rewritten H[k-half h].  The first layer of a tile reads AUX written by both groups.
+        // rewritten H[k-half h].  The first layer of a tile reads AUX written by both groups; so does the first
+        // colour layer of a batched group (all threads bring the parked rows back).
         mbar_wait(&sc->act_ready[0], act_phase);
-        if (st.kind != kStepHidden || si == 0) mbar_wait(&sc->act_ready[1], act_phase);
+        if (st.kind != kStepHidden || si == 0 || (batched && si == P.n_trunk)) mbar_wait(&sc->act_ready[1], act_phase);
         tc_fence_after();
         if (stamp) P.timeline[6 * tl + 0] = clock64();
         if (st.kind == kStepHidden) {
@@ -322,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           const uint64_t dbh_hi = make_desc(s_hhi, 128, kHK * 16), dbh_lo = make_desc(s_hlo, 128, kHK * 16);
           // images only: the colour trunk (every hidden step after the distance heads) needs no
           // Jacobian rows - the value rows are rows 0..31 of the same operands
-          const uint32_t idesc = (P.eval && si > P.head_da_step) ? kIdescHiddenValue : kIdescHidden;
+          const uint32_t idesc = (P.eval && si > P.head_da_step && !batched) ? kIdescHiddenValue : kIdescHidden;
           // One asm block per chunk (a single elect, three MMAs, the commit that frees the ring
           // stage) and no per-iteration selects: the issuing warp shares its scheduler with six other
           // warps, and every instruction between two chunks is tensor-core idle time once the MMA
@@ -350,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             if (h_begin < ks_end) run(d, dbh_hi + (h_begin - nA) * 16, dbh_lo + (h_begin - nA) * 16, ks_end - h_begin, acc);
           };
           issue(0, 0, n0);
-          if (si != 0) {  // accumulator 1 free, H[k >= 128] ready
+          if (si != 0 && !(batched && si == P.n_trunk)) {  // accumulator 1 free, H[k >= 128] ready
             mbar_wait(&sc->act_ready[1], act_phase);
             tc_fence_after();
           }
@@ -377,8 +414,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         act_phase ^= 1;
         if (stamp) {
           P.timeline[6 * tl + 1] = clock64();
-          P.timeline[6 * tl + 4] = 0;
+          P.timeline[6 * tl + 4] = si;
         }
+      }
       }
     }
   } else {
@@ -417,30 +455,78 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
       for (int k = p.n_e0 + p.n_d + 3 + sub; k < kAuxK; k += 16)
         store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad, rows);
     };
+    const bool batched = P.batch > 1;
+    unsigned char* stash = P.stash ? P.stash + (size_t)blockIdx.x * (kMaxBatch * kStashSlot) : nullptr;
+    auto tile_of = [&](int64_t t) { return (int64_t)blockIdx.x + t * gridDim.x; };
+    // batched mode: the colour inputs E0 | D of the tile's samples go straight to its stash slot (value rows,
+    // operand layout), because AUX already takes the next tile's position embedding while the trunk finishes
+    auto stash_value = [&](unsigned char* slot_aux_hi, int s, int k, float v) {
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      bad = fmaxf(bad, fabsf(v));
+      const uint32_t off = act_off(s, k, kAuxK);  // rows 0..31: the first four row groups
+      *reinterpret_cast<__half*>(slot_aux_hi + off) = hi;
+      *reinterpret_cast<__half*>(slot_aux_hi + kStashAux + off) = lo;
+    };
+    auto colour_prep_stash = [&](int slot) {
+      unsigned char* a_hi = stash + (size_t)slot * kStashSlot + 2 * kStashH;
+      const int s = tid >> 4, sub = tid & 15;
+      const int half3 = 3 * p.embed_pos;
+      for (int idx = sub; idx < half3; idx += 16) {  // E0: plain position embedding (neddf.py:205-209)
+        int e = idx / 3, d = idx - 3 * e;
+        PeEntry q = pe_entry(e, sc->geo[s][d], sc->geo[s][6 + d], p.lowpass[e]);
+        stash_value(a_hi, s, idx, q.scale_0 * q.s);
+        stash_value(a_hi, s, half3 + idx, q.scale_0 * q.c);
+      }
+      const int dhalf = 3 * p.embed_dir;
+      for (int idx = sub; idx < dhalf; idx += 16) {
+        int e = idx / 3, d = idx - 3 * e;
+        float sn, cs;
+        sincosf((float)(1u << e) * sc->geo[s][3 + d], &sn, &cs);
+        stash_value(a_hi, s, p.n_e0 + idx, sn);
+        stash_value(a_hi, s, p.n_e0 + dhalf + idx, cs);
+      }
+      // (the K padding above n_e0 + n_d + 3 of the stash was zeroed when it was allocated and is never written)
+    };
+    // 16-byte copies between shared memory and the stash, all epilogue threads
+    auto copy_block = [&](unsigned char* dst, const unsigned char* src, uint32_t bytes, bool from_global) {
+      for (uint32_t o = tid * 16; o < bytes; o += kEpiThreads * 16) {
+        const uint4 v = from_global ? __ldcg(reinterpret_cast<const uint4*>(src + o)) : *reinterpret_cast<const uint4*>(src + o);
+        *reinterpret_cast<uint4*>(dst + o) = v;
+      }
+    };
     if (my_tiles > 0) {
       prologue(blockIdx.x);
       fence_async_smem();
       mbar_arrive(&sc->act_ready[half]);
     }
 
-    for (int64_t t = 0; t < my_tiles; ++t) {
-      const int64_t tile = blockIdx.x + t * gridDim.x;
+    int tl = 0;  // step instance counter (profiling stamps)
+    for (int64_t t0 = 0; t0 < my_tiles; t0 += P.batch) {
+      const int ng = (int)((my_tiles - t0 < P.batch) ? my_tiles - t0 : P.batch);
+      for (int ti = 0; ti <= ng; ++ti) {  // ti == ng: the colour steps of the group
+      const int si_begin = ti < ng ? 0 : P.n_trunk, si_end = ti < ng ? P.n_trunk : P.n_steps;
+      // trunk steps: the tile; colour steps of the per-tile program: the same tile (batched: slot k <-> tile t0 + k)
+      const int64_t tile = tile_of(t0 + (ti < ng ? ti : ng - 1));
       const int64_t n0 = tile * kTileS;
-      for (int si = 0; si < P.n_steps; ++si) {
+      const bool more_tiles = t0 + ng < my_tiles;
+      for (int si = si_begin; si < si_end; ++si, ++tl) {
         const Step& st = P.step[si];
+        const bool more = more_tiles || ti < ng || si + 1 < P.n_steps;  // another step follows
         // one thread per group polls the mbarrier; the rest sleep in a hardware named barrier
         if (lane == 0 && quarter == 0 && shalf == 0) mbar_wait(&sc->acc_ready[half], acc_phase);
         if (half == 0) asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads / 2) : "memory");
         else asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads / 2) : "memory");
         acc_phase ^= 1;
         tc_fence_after();
-        const int tl = (int)(t * P.n_steps + si);
         const bool stamp = P.timeline && blockIdx.x == 0 && tid == 0 && (tl + 1) * 6 <= P.timeline_cap;
         if (stamp) P.timeline[6 * tl + 2] = clock64();
         if (st.kind == kStepHidden) {
           const float bias = __ldg(P.bias + st.bias_off + ch);
           const uint32_t tbase = tmem + lane_addr + half * kRows;
-          const bool value_only = P.eval && si > P.head_da_step;
+          const bool colour = si > P.head_da_step;
+          const bool value_only = P.eval && colour && !batched;
+          const bool all_value = batched && colour;  // the four row blocks are the value rows of four tiles
 #pragma unroll 1
           for (int blk = (P.debug & 8) ? 2 : 0; blk < 2; ++blk) {  // 8 samples = one 16-byte row group per row type
             const int s0 = 16 * shalf + 8 * blk;
@@ -472,8 +558,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                   for (int i = 0; i < 8; ++i)
                     if (n0 + s0 + i < n_total) save[((size_t)i * 4 + j) * kWidth] = g[i];
                 }
+                if (all_value) {
+                  float dd;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) split2h(d1[2 * i] * g[2 * i], d1[2 * i + 1] * g[2 * i + 1], h[i], l[i], badh);
+                  for (int i = 0; i < 8; ++i) tc_hidden_act<ACT>(g[i] + bias, g[i], dd);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) g[i] *= d1[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2h(g[2 * i], g[2 * i + 1], h[i], l[i], badh);
                 off += 4 * (kHK * 16);
                 *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -501,14 +595,75 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
               aux[0] += __ldg(p.b_head + 1);
               HeadOut h;
               head_density(ddf, aux, p.d_near, p.aux_grad_scale, p.density_act, h);
-              sc->head[s] = h;
               const int kn = p.n_e0 + p.n_d;  // normal: detached, zero Jacobian (neddf.py:243-253)
+              if (batched) {
+                // images only: the distance-side outputs leave now, the normal joins the parked colour inputs
+                unsigned char* a_hi = stash + (size_t)ti * kStashSlot + 2 * kStashH;
 #pragma unroll
-              for (int i = 0; i < 3; ++i)
-                store_sample(aux_hi, aux_lo, kAuxK, s, kn + i, h.normal[i], 0.f, 0.f, 0.f, bad, P.eval ? 1 : 4);
+                for (int i = 0; i < 3; ++i) stash_value(a_hi, s, kn + i, h.normal[i]);
+                const int64_t n = n0 + s;
+                if (n < n_total) {
+                  int64_t ray_, on;
+                  int j_;
+                  field_map(p, n, ray_, j_, on);
+                  if (p.distance) p.distance[on] = h.distance;
+                  if (p.density) p.density[on] = h.density;
+                  if (p.aux_grad) p.aux_grad[on] = h.aux;
+                }
+              } else {
+                sc->head[s] = h;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                  store_sample(aux_hi, aux_lo, kAuxK, s, kn + i, h.normal[i], 0.f, 0.f, 0.f, bad, P.eval ? 1 : 4);
+              }
             }
           }
-          if (st.post == 1) colour_prep();  // only when no earlier MMA phase could hide it
+          if (batched) {
+            if (st.post == 1) {  // no earlier MMA phase could hide it
+              colour_prep_stash(ti);
+              if (ti + 1 < ng) {
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // everyone is done with this tile's geometry
+                prologue(tile_of(t0 + ti + 1));
+              }
+            }
+            // park the value rows of the tile's features (rows 0..31 = the first four row groups of H)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the last trunk layer's rows, all threads'
+            unsigned char* slot = stash + (size_t)ti * kStashSlot;
+            copy_block(slot, h_hi, kStashH, false);
+            copy_block(slot + kStashH, h_lo, kStashH, false);
+            if (ti + 1 == ng) {
+              __threadfence();  // this thread's parked rows (plain global stores) before the others read them back
+              // group complete: every slot comes back as rows 32 slot + sample of H and AUX (the heads' MMAs have
+              // finished reading H: their commit is what released this epilogue)
+              asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+              // (all slots, also those a short last group does not use: their rows are old but finite, whereas
+              // never-written shared memory could trip the fp16 range check)
+              for (int k = 0; k < P.batch; ++k) {
+                const unsigned char* src = stash + (size_t)k * kStashSlot;
+                copy_block(h_hi + k * kStashH, src, kStashH, true);
+                copy_block(h_lo + k * kStashH, src + kStashH, kStashH, true);
+                copy_block(aux_hi + k * kStashAux, src + 2 * kStashH, kStashAux, true);
+                copy_block(aux_lo + k * kStashAux, src + 2 * kStashH + kStashAux, kStashAux, true);
+              }
+            }
+          } else if (st.post == 1) {
+            colour_prep();  // only when no earlier MMA phase could hide it
+          }
+        } else if (batched) {
+          // colour head of the group (neddf.py:257): lane quarter = slot, lane = sample
+          if (warp < 4 && quarter < ng) {
+            float v[4];
+            tmem_ld4(tmem + lane_addr + kHeadCol, v);
+            const int64_t n = tile_of(t0 + quarter) * kTileS + lane;
+            if (n < n_total && p.color) {
+              int64_t ray_, on;
+              int j_;
+              field_map(p, n, ray_, j_, on);
+              p.color[3 * on + 0] = v[0] + __ldg(p.b_head + 2);
+              p.color[3 * on + 1] = v[1] + __ldg(p.b_head + 3);
+              p.color[3 * on + 2] = v[2] + __ldg(p.b_head + 4);
+            }
+          }
         } else {
           // colour head (neddf.py:257) + penalties (:259-300) + outputs
           if (warp < 4) {
@@ -547,12 +702,32 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         }
         tc_fence_before();
         fence_async_smem();
-        if (stamp) P.timeline[6 * tl + 3] = clock64();
-        if (t + 1 < my_tiles || si + 1 < P.n_steps) mbar_arrive(&sc->act_ready[half]);
+        if (stamp) {
+          P.timeline[6 * tl + 3] = clock64();
+          P.timeline[6 * tl + 5] = si;
+        }
+        if (more) mbar_arrive(&sc->act_ready[half]);
         // work that only feeds later steps runs here, under the next step's MMA phase; its
         // shared-memory writes are published by the fence + arrive of the following steps
-        if (st.kind == kStepHidden && st.post == 1) colour_prep();
-        if (st.post == 2 && t + 1 < my_tiles) prologue(tile + gridDim.x);
+        if (st.kind == kStepHidden && st.post == 1) {
+          if (batched) {
+            colour_prep_stash(ti);
+            if (ti + 1 < ng) {  // AUX is free from here: the rest of the trunk reads H only
+              asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // everyone is done with this tile's geometry
+              prologue(tile_of(t0 + ti + 1));
+            }
+          } else {
+            colour_prep();
+          }
+        }
+        if (st.post == 2) {
+          if (batched) {
+            if (more_tiles) prologue(tile_of(t0 + ng));
+          } else if (more_tiles) {
+            prologue(tile_of(t0 + 1));
+          }
+        }
+      }
       }
     }
     {
@@ -638,6 +813,8 @@ struct TcStorage {
   long long* timeline = nullptr;
   int timeline_cap = 0;
   int head_da_step = 0;
+  int chunks_trunk = 0;
+  unsigned char* d_stash = nullptr;  // batched colour trunk: parked value rows, kMaxBatch slots per CTA
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -943,6 +1120,7 @@ static int32_t tc_ensure(neddf_field* f) {
       if (head_da >= 0 && first_col < 0 && S->step[i].kind == tc::kStepHidden) first_col = i;
     }
     S->head_da_step = head_da;
+    S->chunks_trunk = S->pack.chunk0[f->n_ddf];
     if (last_aux + 1 < head_da) S->step[last_aux].post = 1;
     else S->step[head_da].post = 1;
     // after the first colour layer's epilogue AUX is dead again: next tile's prologue goes there
@@ -950,11 +1128,14 @@ static int32_t tc_ensure(neddf_field* f) {
   }
   if (cudaMalloc(&S->d_w, (size_t)(chunk + 4) * tc::kChunkBytes) != cudaSuccess ||
       cudaMalloc(&S->d_bias, (size_t)n_hidden * kWidth * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&S->d_stash, (size_t)sm_count() * tc::kMaxBatch * tc::kStashSlot) != cudaSuccess) {
+    cudaFree(S->d_w); cudaFree(S->d_bias); cudaFree(S->d_status); cudaFree(S->d_stash);
     delete S;
     return fail(NEDDF_E_CUDA, "tensor-core engine: cudaMalloc failed");
   }
   cudaMemset(S->d_status, 0, sizeof(int));
+  cudaMemset(S->d_stash, 0, (size_t)sm_count() * tc::kMaxBatch * tc::kStashSlot);  // the K padding of the parked colour inputs stays zero
   f->tc = S;
   return NEDDF_OK;
 }
@@ -965,6 +1146,7 @@ void tc_destroy(neddf_field* f) {
   cudaFree(S->d_w);
   cudaFree(S->d_bias);
   cudaFree(S->d_status);
+  cudaFree(S->d_stash);
   delete S;
   f->tc = nullptr;
 }
@@ -999,6 +1181,12 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
   P.status = S->d_status;
   P.eval = (flags == NEDDF_OUT_EVAL && p.penalty == nullptr) ? 1 : 0;
   P.head_da_step = S->head_da_step;
+  P.n_trunk = S->head_da_step + 1;
+  P.chunks_trunk = S->chunks_trunk;
+  // images only: one colour-trunk pass per four tiles (NEDDF_TC_BATCH=1 keeps the per-tile program)
+  P.batch = (P.eval && p.save_pre == nullptr) ? tc::kMaxBatch : 1;
+  if (const char* e = std::getenv("NEDDF_TC_BATCH")) P.batch = std::max(1, std::min(P.batch, std::atoi(e)));
+  P.stash = S->d_stash;
   P.debug = 0;
   if (const char* e = std::getenv("NEDDF_TC_DEBUG")) {
     P.debug = std::atoi(e);

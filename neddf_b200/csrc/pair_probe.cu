@@ -133,7 +133,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
   const uint32_t peer = mapa_u32(local, rank ^ 1u);
   for (int i = tid; i < bytes / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   cluster_sync_all();
-  const bool active = (mode == 0) || (mode == 1) || (mode == 3) || (mode == 2 && rank == 0);
+  // modes 4 / 5: 8-byte stores at 16-byte stride / only 8 of the 16 warps store (the pair kernel's epilogue patterns)
+  const bool active = (mode == 0) || (mode == 1) || (mode == 3) || (mode == 2 && rank == 0) || (mode == 4) || (mode == 5 && tid < 256);
   const uint32_t base = (mode == 0) ? local : peer;
   long long t0 = clock64();
   if (active) {
@@ -144,7 +145,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
           uint32_t blk = off >> 9, in = off & 511;
           o = (((blk * 5) % (bytes >> 9)) << 9) | in;
         }
-        st_cluster_v4(base + o, make_uint4(r, tid, off, 1));
+        if (mode == 4) st_cluster_v2(base + o, make_uint2(r, tid));
+        else st_cluster_v4(base + o, make_uint4(r, tid, off, 1));
       }
     }
   }
@@ -231,7 +233,7 @@ extern "C" int32_t neddf_tc_pair_selftest(const float* d_a, const float* d_b, in
 
 extern "C" int32_t neddf_dsmem_bench(int32_t mode, int32_t reps, int32_t bytes, int32_t n_clusters, int64_t* d_cycles,
                                      void* stream) {
-  if (mode < 0 || mode > 3 || reps < 1 || bytes < 8192 || bytes > 196608 || (bytes % 8192) != 0 || n_clusters < 1 || !d_cycles)
+  if (mode < 0 || mode > 5 || reps < 1 || bytes < 8192 || bytes > 196608 || (bytes % 8192) != 0 || n_clusters < 1 || !d_cycles)
     return fail(NEDDF_E_INVALID, "neddf_dsmem_bench: bad arguments");
   NEDDF_CUDA_CHECK(cudaFuncSetAttribute(tc::dsmem_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   tc::dsmem_bench_kernel<<<2 * n_clusters, 512, bytes, (cudaStream_t)stream>>>(mode, reps, bytes, reinterpret_cast<long long*>(d_cycles));

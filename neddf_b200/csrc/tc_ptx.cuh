@@ -347,6 +347,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+__device__ __forceinline__ void st_cluster_v2(uint32_t caddr, uint2 v) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1,%2};" ::"r"(caddr), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
