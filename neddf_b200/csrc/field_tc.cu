@@ -49,6 +49,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace neddf {
 namespace tc {
@@ -87,6 +88,7 @@ struct Scratch {
   uint64_t a_empty[kARing];  // MMA -> loaders: chunk consumed
   uint64_t act_ready[2];  // epilogue group h -> MMA: accumulator h drained, H[k-half h] rewritten
   uint64_t acc_ready[2];  // MMA -> epilogue group h: accumulator h complete
+  uint64_t stash_bar;     // bulk copies stash -> H / AUX landed (batched colour trunk)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -131,6 +133,7 @@ constexpr uint32_t kStashH = 4 * kHK * 16;      // four row groups (32 value row
 constexpr uint32_t kStashAux = 4 * kAuxK * 16;  // of AUX: 6 KB
 constexpr uint32_t kStashSlot = 2 * kStashH + 2 * kStashAux;
 constexpr int kMaxBatch = kRows / kTileS;       // 4 slots
+constexpr uint32_t kStashCta = kMaxBatch * kStashSlot;
 
 // ---------------------------------------------------------------------------------------------
 // prologue pieces (epilogue warps)
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
       mbar_init(&sc->act_ready[h], kEpiThreads / 2);
       mbar_init(&sc->acc_ready[h], 1);
     }
+    mbar_init(&sc->stash_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // head weights (B operands of the standard-orientation head MMAs) stay resident: 4 x 8 KB
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad, rows);
     };
     const bool batched = P.batch > 1;
-    unsigned char* stash = P.stash ? P.stash + (size_t)blockIdx.x * (kMaxBatch * kStashSlot) : nullptr;
+    unsigned char* stash = P.stash ? P.stash + (size_t)blockIdx.x * kStashCta : nullptr;
     auto tile_of = [&](int64_t t) { return (int64_t)blockIdx.x + t * gridDim.x; };
     // batched mode: the colour inputs E0 | D of the tile's samples go straight to its stash slot (value rows,
     // operand layout), because AUX already takes the next tile's position embedding while the trunk finishes
@@ -490,9 +494,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     };
     // 16-byte copies between shared memory and the stash, all epilogue threads
     auto copy_block = [&](unsigned char* dst, const unsigned char* src, uint32_t bytes, bool from_global) {
-      for (uint32_t o = tid * 16; o < bytes; o += kEpiThreads * 16) {
-        const uint4 v = from_global ? __ldcg(reinterpret_cast<const uint4*>(src + o)) : *reinterpret_cast<const uint4*>(src + o);
-        *reinterpret_cast<uint4*>(dst + o) = v;
+      if (from_global) {  // L2 latency: four loads in flight per thread
+        for (uint32_t o = tid * 16; o < bytes; o += 4 * kEpiThreads * 16) {
+          uint4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (o + u * kEpiThreads * 16 < bytes) v[u] = __ldcg(reinterpret_cast<const uint4*>(src + o + u * kEpiThreads * 16));
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (o + u * kEpiThreads * 16 < bytes) *reinterpret_cast<uint4*>(dst + o + u * kEpiThreads * 16) = v[u];
+        }
+      } else {
+        for (uint32_t o = tid * 16; o < bytes; o += kEpiThreads * 16) *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(src + o);
       }
     };
     if (my_tiles > 0) {
@@ -502,6 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     }
 
     int tl = 0;  // step instance counter (profiling stamps)
+    uint32_t stash_phase = 0;
     for (int64_t t0 = 0; t0 < my_tiles; t0 += P.batch) {
       const int ng = (int)((my_tiles - t0 < P.batch) ? my_tiles - t0 : P.batch);
       for (int ti = 0; ti <= ng; ++ti) {  // ti == ng: the colour steps of the group
@@ -526,7 +540,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           const uint32_t tbase = tmem + lane_addr + half * kRows;
           const bool colour = si > P.head_da_step;
           const bool value_only = P.eval && colour && !batched;
-          const bool all_value = batched && colour;  // the four row blocks are the value rows of four tiles
+          // batched colour layers: the four row blocks are the value rows of four tiles (compiled as a separate
+          // body: sharing one with the trunk's Jacobian rows made every trunk epilogue ~15 % slower)
+          auto hidden_body = [&](auto all_value_tag) {
+          constexpr bool all_value = decltype(all_value_tag)::value;
 #pragma unroll 1
           for (int blk = (P.debug & 8) ? 2 : 0; blk < 2; ++blk) {  // 8 samples = one 16-byte row group per row type
             const int s0 = 16 * shalf + 8 * blk;
@@ -574,6 +591,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
               }
             }
           }
+          };
+          if (batched && colour) hidden_body(std::true_type{});
+          else hidden_body(std::false_type{});
         } else if (st.kind == kStepHeadDA) {
           if (warp < 4) {
             // lane quarter j = row type j, lane = sample: columns 0,1 = ddf_out, aux_out of that row
@@ -619,13 +639,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             }
           }
           if (batched) {
-            if (st.post == 1) {  // no earlier MMA phase could hide it
-              colour_prep_stash(ti);
-              if (ti + 1 < ng) {
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // everyone is done with this tile's geometry
-                prologue(tile_of(t0 + ti + 1));
-              }
-            }
             // park the value rows of the tile's features (rows 0..31 = the first four row groups of H)
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the last trunk layer's rows, all threads'
             unsigned char* slot = stash + (size_t)ti * kStashSlot;
@@ -637,14 +650,21 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
               // finished reading H: their commit is what released this epilogue)
               asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
               // (all slots, also those a short last group does not use: their rows are old but finite, whereas
-              // never-written shared memory could trip the fp16 range check)
-              for (int k = 0; k < P.batch; ++k) {
-                const unsigned char* src = stash + (size_t)k * kStashSlot;
-                copy_block(h_hi + k * kStashH, src, kStashH, true);
-                copy_block(h_lo + k * kStashH, src + kStashH, kStashH, true);
-                copy_block(aux_hi + k * kStashAux, src + 2 * kStashH, kStashAux, true);
-                copy_block(aux_lo + k * kStashAux, src + 2 * kStashH + kStashAux, kStashAux, true);
+              // never-written shared memory could trip the fp16 range check).  One thread issues the bulk copies.
+              if (tid == 0) {
+                fence_async_all();  // the parked rows were written with ordinary stores
+                mbar_expect_tx(&sc->stash_bar, (uint32_t)P.batch * kStashSlot);
+                for (int k = 0; k < P.batch; ++k) {
+                  const unsigned char* src = stash + (size_t)k * kStashSlot;
+                  tma_bulk_g2s(smem_u32(h_hi + k * kStashH), src, kStashH, &sc->stash_bar);
+                  tma_bulk_g2s(smem_u32(h_lo + k * kStashH), src + kStashH, kStashH, &sc->stash_bar);
+                  tma_bulk_g2s(smem_u32(aux_hi + k * kStashAux), src + 2 * kStashH, kStashAux, &sc->stash_bar);
+                  tma_bulk_g2s(smem_u32(aux_lo + k * kStashAux), src + 2 * kStashH + kStashAux, kStashAux, &sc->stash_bar);
+                }
               }
+              if (lane == 0) mbar_wait(&sc->stash_bar, stash_phase);
+              __syncwarp();
+              stash_phase ^= 1;
             }
           } else if (st.post == 1) {
             colour_prep();  // only when no earlier MMA phase could hide it
@@ -709,16 +729,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         if (more) mbar_arrive(&sc->act_ready[half]);
         // work that only feeds later steps runs here, under the next step's MMA phase; its
         // shared-memory writes are published by the fence + arrive of the following steps
-        if (st.kind == kStepHidden && st.post == 1) {
-          if (batched) {
-            colour_prep_stash(ti);
-            if (ti + 1 < ng) {  // AUX is free from here: the rest of the trunk reads H only
-              asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // everyone is done with this tile's geometry
-              prologue(tile_of(t0 + ti + 1));
-            }
-          } else {
-            colour_prep();
-          }
+        if (batched && ti < ng) {
+          // spread over the trunk so that each piece hides under one layer's MMAs: this tile's colour inputs early,
+          // the next tile's position embedding once AUX is free
+          // (a scattered global write of 2-byte values and a prologue are ~4k cycles each: together they did not fit
+          // under one layer, and the embedding written to global memory instead of AUX took 11k)
+          if (si == 1) colour_prep_stash(ti);
+          if (st.kind == kStepHidden && st.post == 1 && ti + 1 < ng) prologue(tile_of(t0 + ti + 1));  // AUX is free from here
+        } else if (st.kind == kStepHidden && st.post == 1) {
+          colour_prep();
         }
         if (st.post == 2) {
           if (batched) {
@@ -1129,13 +1148,13 @@ static int32_t tc_ensure(neddf_field* f) {
   if (cudaMalloc(&S->d_w, (size_t)(chunk + 4) * tc::kChunkBytes) != cudaSuccess ||
       cudaMalloc(&S->d_bias, (size_t)n_hidden * kWidth * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&S->d_status, sizeof(int)) != cudaSuccess ||
-      cudaMalloc(&S->d_stash, (size_t)sm_count() * tc::kMaxBatch * tc::kStashSlot) != cudaSuccess) {
+      cudaMalloc(&S->d_stash, (size_t)sm_count() * tc::kStashCta) != cudaSuccess) {
     cudaFree(S->d_w); cudaFree(S->d_bias); cudaFree(S->d_status); cudaFree(S->d_stash);
     delete S;
     return fail(NEDDF_E_CUDA, "tensor-core engine: cudaMalloc failed");
   }
   cudaMemset(S->d_status, 0, sizeof(int));
-  cudaMemset(S->d_stash, 0, (size_t)sm_count() * tc::kMaxBatch * tc::kStashSlot);  // the K padding of the parked colour inputs stays zero
+  cudaMemset(S->d_stash, 0, (size_t)sm_count() * tc::kStashCta);  // the K padding of the parked colour inputs stays zero
   f->tc = S;
   return NEDDF_OK;
 }
@@ -1184,7 +1203,11 @@ int32_t launch_field_tc(const neddf_field* f, FieldParams& p, int flags, cudaStr
   P.n_trunk = S->head_da_step + 1;
   P.chunks_trunk = S->chunks_trunk;
   // images only: one colour-trunk pass per four tiles (NEDDF_TC_BATCH=1 keeps the per-tile program)
-  P.batch = (P.eval && p.save_pre == nullptr) ? tc::kMaxBatch : 1;
+  // (needs the trunk's last reader of AUX to be hidden layer 2 or later: the hooks that hide the per-tile work sit
+  // under layer 1 and that one)
+  bool can_batch = false;
+  for (int i = 2; i < S->head_da_step; ++i) can_batch = can_batch || (S->step[i].kind == tc::kStepHidden && S->step[i].post == 1);
+  P.batch = (P.eval && p.save_pre == nullptr && can_batch) ? tc::kMaxBatch : 1;
   if (const char* e = std::getenv("NEDDF_TC_BATCH")) P.batch = std::max(1, std::min(P.batch, std::atoi(e)));
   P.stash = S->d_stash;
   P.debug = 0;

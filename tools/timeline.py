@@ -25,7 +25,7 @@ h = net._field(dev)
 names = ["L0", "L1", "L2", "L3", "L4", "L5", "L6", "HDA", "C0", "C1", "C2", "HCOL"]
 for mode in modes:
     os.environ["NEDDF_TC_DEBUG"] = str(mode)
-    buf = torch.zeros(6 * 12 * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(6 * 160, dtype=torch.int64, device=dev)
     L.check(L.lib().neddf_field_set_timeline(h, L.ptr(buf), buf.numel()))
     render.render_pixels(bench.W, bench.H, cam, ["color"], 1, first, 4096)
     torch.cuda.synchronize()
@@ -38,12 +38,16 @@ for mode in modes:
     t = buf.cpu().view(-1, 6)
     t = t[t[:, 0] != 0]
     print(f"== debug mode {mode}: {rate:.3e} evaluations/s")
-    print("step   mma_issue  wait_full  mma_start->epi_start  epilogue   epi_done->next_mma_start")
-    for i in range(min(len(t) - 1, 24)):
-        if i < 12:
-            continue  # second tile of the CTA: steady state
-        a, b, c, d, wf, _ = [int(x) for x in t[i]]
+    print("step   mma_issue  mma_start->epi_start  epilogue   epi_done->next_mma_start")
+    # the stamps carry the step index (slot 4: MMA warp, slot 5: epilogue); the program is four trunk passes
+    # (L0..HDA) and one colour pass per group when the colour trunk is batched, else all twelve steps per tile
+    batch = int(os.environ.get("NEDDF_TC_BATCH", "4"))
+    per_group = 8 * batch + 4 if batch > 1 else 12
+    lo, hi = per_group, min(len(t) - 1, 2 * per_group)  # second group of the CTA: steady state
+    for i in range(lo, hi):
+        a, b, c, d, si, _ = [int(x) for x in t[i]]
         nxt = int(t[i + 1][0])
-        print(f"{names[i % 12]:5s} {b - a:9d} {wf:9d} {c - a:18d} {d - c:12d} {nxt - d:12d}")
-    tile = int(t[24][0] - t[12][0]) if len(t) > 24 else 0
-    print("cycles per tile:", tile, flush=True)
+        print(f"{names[si]:5s} {b - a:9d} {c - a:18d} {d - c:12d} {nxt - d:12d}")
+    if len(t) > 2 * per_group:
+        grp = int(t[2 * per_group][0] - t[per_group][0])
+        print(f"cycles per group of {batch if batch > 1 else 1} tile(s): {grp}  = {grp // (batch if batch > 1 else 1)} per tile", flush=True)
