@@ -81,7 +81,7 @@ constexpr uint32_t kOffHeadW = kOffAuxLo + kAuxBytes;       // (ddf,aux) hi | lo
 constexpr uint32_t kOffScratch = kOffHeadW + 4 * kChunkBytes;
 
 struct Scratch {
-  float geo[kTileS][12];   // pos[3], dir[3], var[3], pad
+  float geo[2][kTileS][12];   // pos[3], dir[3], var[3], pad; two buffers: the batched program fetches the next tile's early
   HeadOut head[kTileS];
   float hgather[4][kTileS][4];  // head results per row type (lane quarter) and sample
   uint64_t a_full[kARing];   // loaders -> MMA: chunk written to tensor memory
@@ -139,7 +139,7 @@ constexpr uint32_t kStashCta = kMaxBatch * kStashSlot;
 // prologue pieces (epilogue warps)
 // ---------------------------------------------------------------------------------------------
 // geometry of the tile's samples -> scratch (one thread per sample)
-__device__ __forceinline__ void tile_geometry(const FieldParams& p, Scratch* sc, int64_t n0, int s, int64_t n_total) {
+__device__ __forceinline__ void tile_geometry(const FieldParams& p, float (*geo)[12], int64_t n0, int s, int64_t n_total) {
   float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, var[3] = {0.f, 0.f, 0.f};
   const int64_t n = n0 + s;
   if (n < n_total) {
@@ -166,21 +166,21 @@ __device__ __forceinline__ void tile_geometry(const FieldParams& p, Scratch* sc,
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    sc->geo[s][i] = pos[i];
-    sc->geo[s][3 + i] = dir[i];
-    sc->geo[s][6 + i] = var[i];
+    geo[s][i] = pos[i];
+    geo[s][3 + i] = dir[i];
+    geo[s][6 + i] = var[i];
   }
 }
 
 // position embedding of sample s into AUX at K offset k0; scaled = distance-trunk scaling
 // (neddf.py:200-204) else plain (neddf.py:205-209).  `sub`/`nsub` split the 3*E entries.
-__device__ __forceinline__ void write_pos_embedding(const FieldParams& p, const Scratch* sc, unsigned char* aux_hi,
+__device__ __forceinline__ void write_pos_embedding(const FieldParams& p, const float (*geo)[12], unsigned char* aux_hi,
                                                     unsigned char* aux_lo, int s, int sub, int nsub, bool scaled,
                                                     float& bad, int rows = 4) {
   const int half = 3 * p.embed_pos;
   for (int idx = sub; idx < half; idx += nsub) {
     int e = idx / 3, d = idx - 3 * e;
-    PeEntry q = pe_entry(e, sc->geo[s][d], sc->geo[s][6 + d], p.lowpass[e]);
+    PeEntry q = pe_entry(e, geo[s][d], geo[s][6 + d], p.lowpass[e]);
     float sc_ = scaled ? q.scale_s : q.scale_0;
     float g = q.freq * sc_;
     float js = g * q.c, jc = -g * q.s;
@@ -347,9 +347,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         const bool stamp = P.timeline && blockIdx.x == 0 && lane == 0 && (tl + 1) * 6 <= P.timeline_cap;
         // act_ready[h] of the previous step: epilogue group h has drained accumulator h and
         // rewritten H[k-half h].  The first layer of a tile reads AUX written by both groups; so does the first
-        // colour layer of a batched group (all threads bring the parked rows back).
+        // colour layer (colour inputs / normals, or the parked rows that all threads bring back).
         mbar_wait(&sc->act_ready[0], act_phase);
-        if (st.kind != kStepHidden || si == 0 || (batched && si == P.n_trunk)) mbar_wait(&sc->act_ready[1], act_phase);
+        // (the heads start on K-half 0 as soon as group 0 has rewritten it and wait for group 1 half way)
+        if (si == 0 || si == P.n_trunk) mbar_wait(&sc->act_ready[1], act_phase);
         tc_fence_after();
         if (stamp) P.timeline[6 * tl + 0] = clock64();
         if (st.kind == kStepHidden) {
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             if (h_begin < ks_end) run(d, dbh_hi + (h_begin - nA) * 16, dbh_lo + (h_begin - nA) * 16, ks_end - h_begin, acc);
           };
           issue(0, 0, n0);
-          if (si != 0 && !(batched && si == P.n_trunk)) {  // accumulator 1 free, H[k >= 128] ready
+          if (si != 0 && si != P.n_trunk) {  // accumulator 1 free, H[k >= 128] ready
             mbar_wait(&sc->act_ready[1], act_phase);
             tc_fence_after();
           }
@@ -407,6 +408,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           uint64_t da_hi = make_desc(s_hhi, 128, kHK * 16), da_lo = make_desc(s_hlo, 128, kHK * 16);
           uint64_t db_hi = make_desc(w, 128, 4096), db_lo = make_desc(w + kChunkBytes, 128, 4096);
           for (int ks = 0; ks < kHK / 16; ++ks) {
+            if (ks == kHK / 32) {  // H[k >= 128] is group 1's
+              mbar_wait(&sc->act_ready[1], act_phase);
+              tc_fence_after();
+            }
             mma_f16_elect(d, da_hi, db_hi, kIdescHead, ks > 0);
             mma_f16_elect(d, da_lo, db_hi, kIdescHead, 1);
             mma_f16_elect(d, da_hi, db_lo, kIdescHead, 1);
@@ -434,12 +439,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     __half2 badh = __floats2half2_rn(0.f, 0.f);  // same for the hidden layers' operands, on packed hi halves
     uint32_t acc_phase = 0;
 
-    auto prologue = [&](int64_t tile) {
-      const int64_t n0 = tile * kTileS;
-      if (tid < kTileS) tile_geometry(p, sc, n0, tid, n_total);
+    int gcur = 0;  // geometry buffer of the tile in flight
+    // position embedding of the tile whose geometry is in buffer gcur -> AUX (all four row types)
+    auto prologue_pe = [&]() {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const int s = tid >> 4, sub = tid & 15;
-      write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 16, true, bad);
+      write_pos_embedding(p, sc->geo[gcur], aux_hi, aux_lo, s, sub, 16, true, bad);
+      for (int k = p.n_e0 + sub; k < 64; k += 16) store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
+    };
+    auto prologue = [&](int64_t tile) {
+      const int64_t n0 = tile * kTileS;
+      if (tid < kTileS) tile_geometry(p, sc->geo[gcur], n0, tid, n_total);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      const int s = tid >> 4, sub = tid & 15;
+      write_pos_embedding(p, sc->geo[gcur], aux_hi, aux_lo, s, sub, 16, true, bad);
       // zero the K padding of E_s (its weights are zero, the operand must still be finite)
       for (int k = p.n_e0 + sub; k < 64; k += 16) store_sample(aux_hi, aux_lo, kAuxK, s, k, 0.f, 0.f, 0.f, 0.f, bad);
     };
@@ -447,12 +460,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     auto colour_prep = [&]() {
       const int s = tid >> 4, sub = tid & 15;
       const int rows = P.eval ? 1 : 4;
-      write_pos_embedding(p, sc, aux_hi, aux_lo, s, sub, 16, false, bad, rows);
+      write_pos_embedding(p, sc->geo[gcur], aux_hi, aux_lo, s, sub, 16, false, bad, rows);
       const int dhalf = 3 * p.embed_dir;
       for (int idx = sub; idx < dhalf; idx += 16) {
         int e = idx / 3, d = idx - 3 * e;
         float sn, cs;
-        sincosf((float)(1u << e) * sc->geo[s][3 + d], &sn, &cs);
+        sincosf((float)(1u << e) * sc->geo[gcur][s][3 + d], &sn, &cs);
         store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + idx, sn, 0.f, 0.f, 0.f, bad, rows);
         store_sample(aux_hi, aux_lo, kAuxK, s, p.n_e0 + dhalf + idx, cs, 0.f, 0.f, 0.f, bad, rows);
       }
@@ -478,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
       const int half3 = 3 * p.embed_pos;
       for (int idx = sub; idx < half3; idx += 16) {  // E0: plain position embedding (neddf.py:205-209)
         int e = idx / 3, d = idx - 3 * e;
-        PeEntry q = pe_entry(e, sc->geo[s][d], sc->geo[s][6 + d], p.lowpass[e]);
+        PeEntry q = pe_entry(e, sc->geo[gcur][s][d], sc->geo[gcur][s][6 + d], p.lowpass[e]);
         stash_value(a_hi, s, idx, q.scale_0 * q.s);
         stash_value(a_hi, s, half3 + idx, q.scale_0 * q.c);
       }
@@ -486,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
       for (int idx = sub; idx < dhalf; idx += 16) {
         int e = idx / 3, d = idx - 3 * e;
         float sn, cs;
-        sincosf((float)(1u << e) * sc->geo[s][3 + d], &sn, &cs);
+        sincosf((float)(1u << e) * sc->geo[gcur][s][3 + d], &sn, &cs);
         stash_value(a_hi, s, p.n_e0 + idx, sn);
         stash_value(a_hi, s, p.n_e0 + dhalf + idx, cs);
       }
@@ -734,8 +747,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
           // the next tile's position embedding once AUX is free
           // (a scattered global write of 2-byte values and a prologue are ~4k cycles each: together they did not fit
           // under one layer, and the embedding written to global memory instead of AUX took 11k)
-          if (si == 1) colour_prep_stash(ti);
-          if (st.kind == kStepHidden && st.post == 1 && ti + 1 < ng) prologue(tile_of(t0 + ti + 1));  // AUX is free from here
+          if (si == 1) {
+            colour_prep_stash(ti);
+            // the next tile's geometry (dependent global loads) into the other buffer, long before it is needed
+            if (ti + 1 < ng && tid < kTileS) tile_geometry(p, sc->geo[gcur ^ 1], tile_of(t0 + ti + 1) * kTileS, tid, n_total);
+          }
+          if (st.kind == kStepHidden && st.post == 1 && ti + 1 < ng) {  // AUX is free from here
+            gcur ^= 1;
+            prologue_pe();
+          }
         } else if (st.kind == kStepHidden && st.post == 1) {
           colour_prep();
         }
