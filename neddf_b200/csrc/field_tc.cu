@@ -183,12 +183,11 @@ __device__ __forceinline__ void write_pos_embedding(const FieldParams& p, const 
     PeEntry q = pe_entry(e, geo[s][d], geo[s][6 + d], p.lowpass[e]);
     float sc_ = scaled ? q.scale_s : q.scale_0;
     float g = q.freq * sc_;
-    float js = g * q.c, jc = -g * q.s;
-    float vs[4] = {sc_ * q.s, 0.f, 0.f, 0.f}, vc[4] = {sc_ * q.c, 0.f, 0.f, 0.f};
-    vs[1 + d] = js;
-    vc[1 + d] = jc;
-    store_sample(aux_hi, aux_lo, kAuxK, s, idx, vs[0], vs[1], vs[2], vs[3], bad, rows);
-    store_sample(aux_hi, aux_lo, kAuxK, s, half + idx, vc[0], vc[1], vc[2], vc[3], bad, rows);
+    // the Jacobian of entry (e, d) is non-zero in row type 1 + d only (selects, not an indexed local array: that
+    // array lived in local memory and the prologue was several thousand cycles of LDL / STL round trips)
+    const float js = g * q.c, jc = -g * q.s;
+    store_sample(aux_hi, aux_lo, kAuxK, s, idx, sc_ * q.s, d == 0 ? js : 0.f, d == 1 ? js : 0.f, d == 2 ? js : 0.f, bad, rows);
+    store_sample(aux_hi, aux_lo, kAuxK, s, half + idx, sc_ * q.c, d == 0 ? jc : 0.f, d == 1 ? jc : 0.f, d == 2 ? jc : 0.f, bad, rows);
   }
 }
 

@@ -831,3 +831,46 @@ def test_sample_pdf_without_coarse_edges():
     o = out.cpu()
     assert bool((o[:, 1:] >= o[:, :-1]).all())
     render._status_buf.zero_()
+
+
+@pytest.mark.parametrize("n_rays", [1, 3, 37, 600, 2500])
+def test_tc_batched_colour_trunk_matches_per_tile_program(n_rays, monkeypatch):
+    """Images-only launches of the tc engine run the colour trunk once per group of four tiles
+    (TcParams::batch, DESIGN 4.1).  Same results as the per-tile program (NEDDF_TC_BATCH=1) for launches
+    with fewer tiles than CTAs, ragged last tiles and groups of 1, 2, 3 and 4 tiles per CTA, and as the
+    oracle (neddf.py:200-257 through oracle.field_forward)."""
+    import neddf_b200
+    G = _gpu()
+    c = Case("bunny")
+    render = G.build_render(c, "tc")
+    net = render.network_fine
+    g = torch.Generator().manual_seed(n_rays)
+    uv = torch.stack([torch.randint(0, 50, (n_rays,), generator=g), torch.randint(0, 50, (n_rays,), generator=g)], 1).float()
+    d, o = orc.make_rays(uv, c.cam)
+    dists = orc.coarse_dists(c.rc, torch.rand(n_rays, c.rc.sample_coarse + 1, generator=g))
+    radius = neddf_b200.ray.CONE_RAY_RADIUS if c.rc.sampling_type == "cone" else 0.0
+
+    def run():
+        with torch.no_grad():
+            out = net.forward_rays(d.to(G.DEV), o.to(G.DEV), dists.to(G.DEV), c.rc.sampling_type, radius,
+                                   need_penalty=False, need_aux=True)
+        torch.cuda.synchronize()
+        net.check_engine_status()
+        return {k: v.cpu() for k, v in out.items()}
+
+    batched = run()
+    monkeypatch.setenv("NEDDF_TC_BATCH", "1")
+    per_tile = run()
+    monkeypatch.delenv("NEDDF_TC_BATCH")
+    for k in ("density", "distance", "aux_grad"):
+        assert torch.equal(batched[k], per_tile[k]), k  # the distance trunk is the same program
+    # colour: N = 128 instead of N = 32 MMAs over the same operands
+    assert nerr(batched["color"].numpy(), per_tile["color"].numpy()) < 1e-6
+    pos, dd, var = orc.make_samples(c.rc, d, o, dists)
+    with torch.no_grad():
+        ref = orc.field_forward(c.p_fine, c.fc, c.st, pos, dd, var)
+    # (random pixels mostly look past the bunny: densities of 1e-2 and below, for which max|ref| is no scale -
+    # the floor of 1 keeps the bound absolute there; colours are O(1))
+    for k in ("density", "color"):
+        a, r = batched[k].numpy(), ref[k].numpy()
+        assert np.abs(a - r).max() <= PARITY_TOL * max(np.abs(r).max(), 1.0), k
