@@ -101,7 +101,10 @@ const char* neddf_last_error(void);
 int32_t neddf_field_layer_shapes(const neddf_field_config_t* cfg, int32_t* shapes_out, int32_t max_layers);
 
 /* NeDDF.__init__ (neddf.py:52-160): validates the configuration, allocates packed-weight
- * storage on the current device. */
+ * storage on the current device.  A handle also owns per-launch scratch of its kernels (status word, the parked
+ * rows of the batched colour trunk, head partial sums of the pair kernel): launches on ONE handle must be
+ * stream-ordered with respect to each other (the reference's module is not re-entrant either); different
+ * handles - e.g. the coarse and the fine network - are independent. */
 int32_t neddf_field_create(const neddf_field_config_t* cfg, neddf_field_t** out);
 int32_t neddf_field_destroy(neddf_field_t* f);
 
