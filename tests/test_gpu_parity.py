@@ -833,17 +833,21 @@ def test_sample_pdf_without_coarse_edges():
     render._status_buf.zero_()
 
 
-@pytest.mark.parametrize("n_rays", [1, 3, 37, 600, 2500])
-def test_tc_batched_colour_trunk_matches_per_tile_program(n_rays, monkeypatch):
+@pytest.mark.parametrize("case,n_rays", [("bunny", 1), ("bunny", 3), ("bunny", 37), ("bunny", 600), ("bunny", 2500),
+                                         ("default", 600), ("point", 600), ("leaky", 600)])
+def test_tc_batched_colour_trunk_matches_per_tile_program(case, n_rays, monkeypatch):
     """Images-only launches of the tc engine run the colour trunk once per group of four tiles
     (TcParams::batch, DESIGN 4.1).  Same results as the per-tile program (NEDDF_TC_BATCH=1) for launches
-    with fewer tiles than CTAs, ragged last tiles and groups of 1, 2, 3 and 4 tiles per CTA, and as the
-    oracle (neddf.py:200-257 through oracle.field_forward)."""
+    with fewer tiles than CTAs, ragged last tiles and groups of 1, 2, 3 and 4 tiles per CTA, for every golden
+    configuration (activations, skips, sampling types), and as the oracle (neddf.py:200-257 through
+    oracle.field_forward)."""
     import neddf_b200
     G = _gpu()
-    c = Case("bunny")
+    c = Case(case)
     render = G.build_render(c, "tc")
     net = render.network_fine
+    if net.resolved_engine(G.DEV) != "tc":
+        pytest.skip("this configuration does not run on the tc engine")
     g = torch.Generator().manual_seed(n_rays)
     uv = torch.stack([torch.randint(0, 50, (n_rays,), generator=g), torch.randint(0, 50, (n_rays,), generator=g)], 1).float()
     d, o = orc.make_rays(uv, c.cam)
@@ -873,4 +877,8 @@ def test_tc_batched_colour_trunk_matches_per_tile_program(n_rays, monkeypatch):
     # the floor of 1 keeps the bound absolute there; colours are O(1))
     for k in ("density", "color"):
         a, r = batched[k].numpy(), ref[k].numpy()
-        assert np.abs(a - r).max() <= PARITY_TOL * max(np.abs(r).max(), 1.0), k
+        e = np.abs(a.astype(np.float64) - r) / max(np.abs(r).max(), 1.0)
+        if c.kinked:  # same allowance as helpers.assert_parity: the few samples within rounding distance of a kink
+            assert int((e >= PARITY_TOL).sum()) <= max(2, int(1e-2 * e.size)) and e.max() < 5e-2, (k, e.max())
+        else:
+            assert e.max() < PARITY_TOL, (k, e.max())
