@@ -615,3 +615,86 @@ def split_matmul(fmt: str, products: int = 3) -> MatMul:
         return out
 
     return mm
+
+
+# --------------------------------------------------------------------------------------
+# the NeRF field variant: same renderer, plain MLP, no Jacobian rows
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class NerfConfig:
+    """Constructor arguments of NeRF (neddf/network/nerf.py:34-44)."""
+
+    embed_pos_rank: int = 10
+    embed_dir_rank: int = 4
+    layer_count: int = 8
+    layer_width: int = 256
+    activation_type: str = "ReLU"
+    density_activation_type: str = "ReLU"
+    skips: Optional[List[int]] = None
+    lowpass_alpha_offset: float = 10.0
+
+    def __post_init__(self) -> None:
+        if self.skips is None:
+            self.skips = [4]
+
+    @staticmethod
+    def from_dict(d: Dict) -> "NerfConfig":
+        d = {k: v for k, v in dict(d).items() if k != "_target_"}
+        if d.get("skips") is not None:
+            d["skips"] = [int(s) for s in d["skips"]]
+        return NerfConfig(**d)
+
+    def lowpass_alpha_at(self, it: int) -> float:
+        """NeRF.set_iter (nerf.py:167-178)."""
+        return float(self.embed_pos_rank) if it == -1 else self.lowpass_alpha_offset + 0.001 * it
+
+
+def nerf_layer_shapes(cfg: NerfConfig) -> List[Tuple[str, int, int]]:
+    """state_dict names and [in,out] shapes of the NeRF linear layers (nerf.py:86-103)."""
+    in_pos, in_dir = cfg.embed_pos_rank * 6, cfg.embed_dir_rank * 6
+    shapes = [("layers.0", in_pos, cfg.layer_width)]
+    for lid in range(cfg.layer_count - 1):
+        shapes.append((f"layers.{lid + 1}", cfg.layer_width + (in_pos if lid in cfg.skips else 0), cfg.layer_width))
+    shapes.append(("outL_density", cfg.layer_width, 1))
+    shapes.append(("outL_color.0", cfg.layer_width + in_dir, cfg.layer_width // 2))
+    shapes.append(("outL_color.2", cfg.layer_width // 2, 3))
+    return shapes
+
+
+def nerf_forward(P: Dict[str, Tensor], cfg: NerfConfig, lowpass_alpha: float, pos: Tensor, dirs: Tensor,
+                 var: Tensor) -> Dict[str, Tensor]:
+    """NeRF.forward (neddf/network/nerf.py:107-165) on a [B,S,3] block of samples.  ``P`` holds the
+    weights as [in,out] (transposed torch Linear weights) under the reference's state_dict names."""
+    B, S = pos.shape[0], pos.shape[1]
+    n = B * S
+    x3, d3, v3 = pos.reshape(n, 3), dirs.reshape(n, 3), var.reshape(n, 3)
+    E = cfg.embed_pos_rank
+    scale = lowpass_scale(E, lowpass_alpha, pos.dtype).reshape(1, E, 1).expand(1, E, 3).reshape(1, 3 * E)
+    scale = scale * pe_weights(v3, E)  # nerf.py:133-141
+    embed_pos = pe_plain(x3, E) * torch.cat([scale, scale], 1)
+    embed_dir = pe_plain(d3, cfg.embed_dir_rank)  # nerf.py:142
+    act = {"ReLU": torch.relu, "LeakyReLU": torch.nn.functional.leaky_relu,
+           "tanhExp": lambda t: density_act("tanhExp", t)}[cfg.activation_type]
+    hx = embed_pos
+    for lid in range(cfg.layer_count):  # nerf.py:144-148
+        hx = act(hx @ P[f"layers.{lid}.weight"] + P[f"layers.{lid}.bias"])
+        if lid in cfg.skips:
+            hx = torch.cat([hx, embed_pos], 1)
+    density = density_act(cfg.density_activation_type, hx @ P["outL_density.weight"] + P["outL_density.bias"])
+    feat = torch.cat([hx, embed_dir], 1)  # nerf.py:151-152
+    c1 = torch.relu(feat @ P["outL_color.0.weight"] + P["outL_color.0.bias"])
+    color = c1 @ P["outL_color.2.weight"] + P["outL_color.2.bias"]
+    return {"density": density.reshape(B, S), "color": color.reshape(B, S, 3)}
+
+
+def nerf_init_params(cfg: NerfConfig, seed: int, bias_std: float = 0.05) -> Dict[str, Tensor]:
+    """Seeded weights [in,out] for tests (the reference uses torch's default Linear init; goldens carry their
+    weights explicitly)."""
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, Tensor] = {}
+    for name, cin, cout in nerf_layer_shapes(cfg):
+        out[name + ".weight"] = torch.randn(cin, cout, generator=g) * math.sqrt(2.0 / (cin + cout))
+        out[name + ".bias"] = torch.randn(cout, generator=g) * bias_std
+    return out
