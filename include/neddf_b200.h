@@ -354,6 +354,48 @@ int32_t neddf_dsmem_bench(int32_t mode, int32_t reps, int32_t bytes, int32_t n_c
  * the 16-bit pattern value[i] = i with descriptor strides (lbo, sbo); d_out[128 lanes][8 columns]. */
 int32_t neddf_tc_cp_probe(int32_t lbo, int32_t sbo, uint32_t* d_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * NeRF field variant (neddf/network/nerf.py).  Forward only, fp32 CUDA-core kernel
+ * (csrc/nerf_simt.cu): the same renderer entry points (coarse_dists, composite, sample_pdf) serve it.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct neddf_nerf_config {
+  int32_t embed_pos_rank;          /* nerf.py:36 (6 * rank <= 64) */
+  int32_t embed_dir_rank;          /* nerf.py:37 (6 * rank <= 32) */
+  int32_t layer_count;             /* nerf.py:38, 2..12 */
+  int32_t layer_width;             /* nerf.py:39, must be 256 */
+  int32_t activation_type;         /* NEDDF_ACT_* (nerf.py:40) */
+  int32_t density_activation_type; /* NEDDF_ACT_* (nerf.py:41) */
+  int32_t n_skips;                 /* nerf.py:42: ids of the layers AFTER which [h | embed_pos] is concatenated */
+  int32_t skips[8];
+} neddf_nerf_config_t;
+
+typedef struct neddf_nerf neddf_nerf_t; /* opaque: config + packed device weights */
+
+/* Number of linear layers and their [in,out] shapes in state_dict order layers.0 .. layers.{L-1}, outL_density,
+ * outL_color.0, outL_color.2 (nerf.py:86-103).  shapes_out receives 2*n int32 (may be NULL). */
+int32_t neddf_nerf_layer_shapes(const neddf_nerf_config_t* cfg, int32_t* shapes_out, int32_t max_layers);
+
+/* NeRF.__init__ (nerf.py:34-105).  NEDDF_E_UNSUPPORTED for widths other than 256 or a skip after the last layer. */
+int32_t neddf_nerf_create(const neddf_nerf_config_t* cfg, neddf_nerf_t** out);
+void neddf_nerf_destroy(neddf_nerf_t* h);
+
+/* Re-pack the weights: d_w[i] / d_b[i] are device pointers to torch nn.Linear tensors ([out,in] row-major and [out])
+ * in the order of neddf_nerf_layer_shapes; n_layers = layer_count + 3.  Call after every change of the parameters. */
+int32_t neddf_nerf_set_weights(neddf_nerf_t* h, const float* const* d_w, const float* const* d_b, int32_t n_layers,
+                               void* stream);
+
+/* NeRF.forward (nerf.py:107-165) on n samples given explicitly (Sampling.sample_pos / sample_dir / sample_var, each
+ * [n,3]).  lowpass = host array [embed_pos_rank] of PositionalEncoding.get_lowpass_scale(lowpass_alpha)
+ * (positional_encoding.py:67-89).  Outputs density [n], color [n,3] (raw, the renderer applies the range limits). */
+int32_t neddf_nerf_forward(const neddf_nerf_t* h, const float* lowpass, const float* d_pos, const float* d_dir,
+                           const float* d_var, int64_t n, float* d_density, float* d_color, void* stream);
+
+/* Same with the sample geometry fused (Ray.get_sampling_points / get_sampling_cones, ray.py:88-194): rays [n_rays,3],
+ * dists [n_rays, n_edges]; outputs [n_rays, n_edges] and [n_rays, n_edges, 3]. */
+int32_t neddf_nerf_forward_rays(const neddf_nerf_t* h, const float* lowpass, const float* d_ray_dir, const float* d_ray_orig,
+                                const float* d_dists, int64_t n_rays, int32_t n_edges, int32_t sampling_type,
+                                float ray_radius, float* d_density, float* d_color, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

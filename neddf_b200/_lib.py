@@ -35,6 +35,14 @@ class FieldConfig(C.Structure):
     ]
 
 
+class NerfConfig(C.Structure):
+    _fields_ = [
+        ("embed_pos_rank", C.c_int32), ("embed_dir_rank", C.c_int32), ("layer_count", C.c_int32),
+        ("layer_width", C.c_int32), ("activation_type", C.c_int32), ("density_activation_type", C.c_int32),
+        ("n_skips", C.c_int32), ("skips", C.c_int32 * MAX_SKIPS),
+    ]
+
+
 class FieldState(C.Structure):
     _fields_ = [("aux_grad_scale", C.c_float), ("distance_range_max", C.c_float), ("lowpass_alpha", C.c_float),
                 ("penalty_weight", C.c_float * N_PENALTY)]
@@ -90,6 +98,12 @@ _SIGNATURES = {
     "neddf_tc_pair_selftest": (_I32, [_P, _P, _I32, _I32, _P, _P, _I32, _P]),
     "neddf_tc_cp_probe": (_I32, [_I32, _I32, _P, _P]),
     "neddf_dsmem_bench": (_I32, [_I32, _I32, _I32, _I32, _P, _P]),
+    "neddf_nerf_layer_shapes": (_I32, [C.POINTER(NerfConfig), C.POINTER(C.c_int32), _I32]),
+    "neddf_nerf_create": (_I32, [C.POINTER(NerfConfig), C.POINTER(_P)]),
+    "neddf_nerf_destroy": (None, [_P]),
+    "neddf_nerf_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P]),
+    "neddf_nerf_forward": (_I32, [_P, _FP, _P, _P, _P, _I64, _P, _P, _P]),
+    "neddf_nerf_forward_rays": (_I32, [_P, _FP, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
 }
 
 _lib = None

@@ -20,6 +20,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _lib as L
+from .nerf import NeRF
 from .network import BaseNeuralField, NeDDF
 from .ray import CONE_RAY_RADIUS, Ray
 
@@ -28,6 +29,11 @@ _TARGET_ALIASES = {
     "neddf.network.neddf.NeDDF": NeDDF,
     "neddf_b200.NeDDF": NeDDF,
     "neddf_b200.network.NeDDF": NeDDF,
+    # the NeRF field variant: forward / image rendering on the CUDA kernel of nerf.py
+    "neddf.network.NeRF": NeRF,
+    "neddf.network.nerf.NeRF": NeRF,
+    "neddf_b200.NeRF": NeRF,
+    "neddf_b200.nerf.NeRF": NeRF,
 }
 
 
@@ -39,8 +45,8 @@ def _instantiate(network_config) -> BaseNeuralField:
     cls = _TARGET_ALIASES.get(target)
     if cls is None:
         raise NotImplementedError(
-            f"neddf_b200.NeRFRender accelerates the NeDDF field only; network _target_={target!r} "
-            "(NeRF / NeuS) is outside the B200 hot path - use the reference renderer for it")
+            f"neddf_b200.NeRFRender runs the NeDDF field and the NeRF variant; network _target_={target!r} "
+            "(NeuS) is outside the B200 hot path - use the reference renderer for it")
     for k in ("skips",):
         if cfg.get(k) is not None:
             cfg[k] = [int(s) for s in cfg[k]]
@@ -308,7 +314,8 @@ class NeRFRender(BaseNeuralRender):
                                               need_penalty=full, need_aux=False)
         ic = self.integrate_volume_render(dists_c, vc["density"], vc["color"], vc.get("fields_penalty"))
         dists_f = self.sample_pdf(dists_c, ic["weight"], Ef_new, uniform_rands=u_fine)
-        if not full and self.transmittance_eps > 0.0 and not torch.is_grad_enabled():
+        if (not full and self.transmittance_eps > 0.0 and not torch.is_grad_enabled()
+                and hasattr(self.network_fine, "forward_rays_segment")):
             vf = self._fine_pass_terminated(ray_dir, ray_orig, dists_f)
         else:
             vf = self.network_fine.forward_rays(ray_dir, ray_orig, dists_f, self.sampling_type, self._ray_radius,
