@@ -698,3 +698,139 @@ def nerf_init_params(cfg: NerfConfig, seed: int, bias_std: float = 0.05) -> Dict
         out[name + ".weight"] = torch.randn(cin, cout, generator=g) * math.sqrt(2.0 / (cin + cout))
         out[name + ".bias"] = torch.randn(cout, generator=g) * bias_std
     return out
+
+
+# --------------------------------------------------------------------------------------
+# the NeuS field variant: SDF trunk, one reverse-mode gradient, colour trunk
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class NeusConfig:
+    """Constructor arguments of NeuS (neddf/network/neus.py:29-40)."""
+
+    embed_pos_rank: int = 6
+    embed_dir_rank: int = 4
+    sdf_layer_count: int = 8
+    sdf_layer_width: int = 256
+    col_layer_count: int = 8
+    col_layer_width: int = 256
+    activation_type: str = "ReLU"
+    init_variance: float = 0.3
+    skips: Optional[List[int]] = None
+
+    def __post_init__(self) -> None:
+        if self.skips is None:
+            self.skips = [4]
+
+    @staticmethod
+    def from_dict(d: Dict) -> "NeusConfig":
+        d = {k: v for k, v in dict(d).items() if k != "_target_"}
+        if d.get("skips") is not None:
+            d["skips"] = [int(s) for s in d["skips"]]
+        return NeusConfig(**d)
+
+
+def neus_layer_shapes(cfg: NeusConfig) -> List[Tuple[str, int, int]]:
+    """state_dict names and [in,out] shapes of the NeuS linear layers (neus.py:83-98): layers_sdf.0 .. ,
+    layers_col.0 .. layers_col.{col_layer_count} (the last one is the 3-channel output)."""
+    in_sdf = cfg.embed_pos_rank * 6
+    in_col = 6 + cfg.embed_dir_rank * 6 + cfg.sdf_layer_width
+    shapes = [("layers_sdf.0", in_sdf, cfg.sdf_layer_width)]
+    for lid in range(cfg.sdf_layer_count - 1):
+        shapes.append((f"layers_sdf.{lid + 1}", cfg.sdf_layer_width + (in_sdf if lid in cfg.skips else 0), cfg.sdf_layer_width))
+    shapes.append(("layers_col.0", in_col, cfg.col_layer_width))
+    for i in range(cfg.col_layer_count - 1):
+        shapes.append((f"layers_col.{i + 1}", cfg.col_layer_width, cfg.col_layer_width))
+    shapes.append((f"layers_col.{cfg.col_layer_count}", cfg.col_layer_width, 3))
+    return shapes
+
+
+def _neus_act(name: str) -> Callable[[Tensor], Tensor]:
+    # neus.py:70-75: nn.ReLU or the plain tanhExp autograd Function (nn_module/tanh_exp.py:15-60; its backward
+    # tx - x ex (tx^2 - 1), 1 above the threshold, is the derivative autograd finds for the expression below)
+    return {"ReLU": torch.relu, "tanhExp": lambda t: density_act("tanhExp", t)}[name]
+
+
+def neus_density(sdf: Tensor, variance: Tensor) -> Tensor:
+    """neus.py:150-153, operation by operation."""
+    ex = torch.exp(-variance * 10.0 * sdf)
+    return variance * 10.0 * ex * torch.reciprocal(torch.square(1 + ex))
+
+
+def neus_forward(P: Dict[str, Tensor], cfg: NeusConfig, pos: Tensor, dirs: Tensor) -> Dict[str, Tensor]:
+    """NeuS.forward (neddf/network/neus.py:101-162) on a [B,S,3] block of samples; the normal is the reverse-mode
+    gradient of the SDF with respect to the position, as in the reference (neus.py:133-142).  ``P`` holds the
+    weights as [in,out] under the reference's state_dict names plus ``variance``.  Runs with autograd enabled
+    whatever the caller's mode (the reference fails under no_grad: autograd.grad has nothing to differentiate)."""
+    B, S = pos.shape[0], pos.shape[1]
+    n = B * S
+    act = _neus_act(cfg.activation_type)
+    with torch.enable_grad():
+        x3 = pos.detach().reshape(n, 3).clone().requires_grad_(True)
+        embed_pos = pe_plain(x3, cfg.embed_pos_rank)  # neus.py:119
+        embed_dir = pe_plain(dirs.reshape(n, 3), cfg.embed_dir_rank)  # neus.py:120
+        hx = embed_pos
+        for lid in range(cfg.sdf_layer_count):  # neus.py:122-126
+            hx = act(hx @ P[f"layers_sdf.{lid}.weight"] + P[f"layers_sdf.{lid}.bias"])
+            if lid in cfg.skips:
+                hx = torch.cat([hx, embed_pos], 1)
+        sdf = hx[:, :1]
+        (gradients,) = torch.autograd.grad(sdf, x3, torch.ones_like(sdf), retain_graph=False)  # neus.py:133-142
+    with torch.no_grad():
+        hx = hx.detach()
+        sdf = sdf.detach()
+        hc = torch.cat([x3.detach(), embed_dir, gradients, hx], 1)  # neus.py:144-147
+        for lid in range(cfg.col_layer_count + 1):  # every colour layer is followed by the activation, the last too
+            hc = act(hc @ P[f"layers_col.{lid}.weight"] + P[f"layers_col.{lid}.bias"])
+        density = neus_density(sdf, P["variance"])
+    return {"sdf": sdf.reshape(B, S), "density": density.reshape(B, S), "color": hc.reshape(B, S, 3),
+            "gradients": gradients.reshape(B, S, 3)}
+
+
+def neus_forward_jac(P: Dict[str, Tensor], cfg: NeusConfig, pos: Tensor, dirs: Tensor) -> Dict[str, Tensor]:
+    """The same network with the gradient carried FORWARD (value row + three Jacobian rows through the SDF trunk,
+    the formulation of the CUDA kernel); equal to neus_forward up to rounding, checked in tests/test_neus_oracle.py."""
+    B, S = pos.shape[0], pos.shape[1]
+    n = B * S
+    x3, d3 = pos.reshape(n, 3), dirs.reshape(n, 3)
+    E = cfg.embed_pos_rank
+    embed_pos, embed_J = _pe_plain_jac(x3, E)
+    hidden = {"ReLU": lambda x, J: (torch.relu(x), J * (x > 0).to(x.dtype).unsqueeze(1)), "tanhExp": act_tanhexp}[cfg.activation_type]
+    hx, hJ = embed_pos, embed_J
+    for lid in range(cfg.sdf_layer_count):
+        y, G = linear_jac(hx, hJ, P[f"layers_sdf.{lid}.weight"], P[f"layers_sdf.{lid}.bias"])
+        hx, hJ = hidden(y, G)
+        if lid in cfg.skips:
+            hx, hJ = torch.cat([hx, embed_pos], 1), torch.cat([hJ, embed_J], 2)
+    sdf, gradients = hx[:, :1], hJ[:, :, 0]
+    act = _neus_act(cfg.activation_type)
+    hc = torch.cat([x3, pe_plain(d3, cfg.embed_dir_rank), gradients, hx], 1)
+    for lid in range(cfg.col_layer_count + 1):
+        hc = act(hc @ P[f"layers_col.{lid}.weight"] + P[f"layers_col.{lid}.bias"])
+    density = neus_density(sdf, P["variance"])
+    return {"sdf": sdf.reshape(B, S), "density": density.reshape(B, S), "color": hc.reshape(B, S, 3),
+            "gradients": gradients.reshape(B, S, 3)}
+
+
+def _pe_plain_jac(x3: Tensor, embed_dim: int) -> Tuple[Tensor, Tensor]:
+    """[sin p | cos p] with p[e*3+d] = 2^e x_d and its Jacobian rows J[n, i, k] = d embed_k / d x_i."""
+    n = x3.shape[0]
+    freq = (2.0 ** torch.arange(embed_dim, dtype=x3.dtype)).reshape(1, embed_dim, 1)
+    p = (freq * x3.reshape(n, 1, 3)).reshape(n, embed_dim * 3)
+    fr = freq.expand(1, embed_dim, 3).reshape(1, embed_dim * 3)
+    onehot = torch.eye(3, dtype=x3.dtype).repeat(1, embed_dim).reshape(1, 3, embed_dim * 3)  # [i, e*3+d] = (d == i)
+    Js = (fr * torch.cos(p)).unsqueeze(1) * onehot
+    Jc = (-fr * torch.sin(p)).unsqueeze(1) * onehot
+    return torch.cat([torch.sin(p), torch.cos(p)], 1), torch.cat([Js, Jc], 2)
+
+
+def neus_init_params(cfg: NeusConfig, seed: int, bias_std: float = 0.05) -> Dict[str, Tensor]:
+    """Seeded weights [in,out] + variance for tests (goldens carry their weights explicitly)."""
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, Tensor] = {}
+    for name, cin, cout in neus_layer_shapes(cfg):
+        out[name + ".weight"] = torch.randn(cin, cout, generator=g) * math.sqrt(2.0 / (cin + cout))
+        out[name + ".bias"] = torch.randn(cout, generator=g) * bias_std
+    out["variance"] = torch.tensor(float(cfg.init_variance))
+    return out
