@@ -396,6 +396,52 @@ int32_t neddf_nerf_forward_rays(const neddf_nerf_t* h, const float* lowpass, con
                                 const float* d_dists, int64_t n_rays, int32_t n_edges, int32_t sampling_type,
                                 float ray_radius, float* d_density, float* d_color, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * NeuS field variant (neddf/network/neus.py).  Forward only, fp32 CUDA-core kernel
+ * (csrc/neus_simt.cu + csrc/neus_kernel.cuh); the normal d sdf / d position, which the reference takes with
+ * torch.autograd.grad (neus.py:133-142), is carried forward through the SDF trunk as three Jacobian rows.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct neddf_neus_config {
+  int32_t embed_pos_rank;   /* neus.py:31 (6 * rank <= 64) */
+  int32_t embed_dir_rank;   /* neus.py:32 (6 + 6 * rank <= 32) */
+  int32_t sdf_layer_count;  /* neus.py:33, 1..12 */
+  int32_t sdf_layer_width;  /* neus.py:34, must be 256 */
+  int32_t col_layer_count;  /* neus.py:35, 1..12 (+ the 3-channel output layer) */
+  int32_t col_layer_width;  /* neus.py:36, must be 256 */
+  int32_t activation_type;  /* NEDDF_ACT_RELU | NEDDF_ACT_TANHEXP (neus.py:70-75) */
+  int32_t n_skips;          /* neus.py:39: ids of the SDF layers AFTER which [h | embed_pos] is concatenated */
+  int32_t skips[8];
+} neddf_neus_config_t;
+
+typedef struct neddf_neus neddf_neus_t; /* opaque: config + packed device weights */
+
+/* Number of linear layers and their [in,out] shapes in state_dict order layers_sdf.0 .. layers_sdf.{Ls-1},
+ * layers_col.0 .. layers_col.{Lc} (neus.py:83-98).  shapes_out receives 2*n int32 (may be NULL). */
+int32_t neddf_neus_layer_shapes(const neddf_neus_config_t* cfg, int32_t* shapes_out, int32_t max_layers);
+
+/* NeuS.__init__ (neus.py:29-99).  NEDDF_E_UNSUPPORTED for widths other than 256, activations other than
+ * ReLU / tanhExp or a skip after the last SDF layer. */
+int32_t neddf_neus_create(const neddf_neus_config_t* cfg, neddf_neus_t** out);
+void neddf_neus_destroy(neddf_neus_t* h);
+
+/* Re-pack the weights: d_w[i] / d_b[i] are device pointers to torch nn.Linear tensors ([out,in] row-major and [out])
+ * in the order of neddf_neus_layer_shapes (n_layers = sdf_layer_count + col_layer_count + 1); d_variance = the
+ * scalar `variance` parameter (neus.py:99).  Call after every change of the parameters. */
+int32_t neddf_neus_set_weights(neddf_neus_t* h, const float* const* d_w, const float* const* d_b, int32_t n_layers,
+                               const float* d_variance, void* stream);
+
+/* NeuS.forward (neus.py:101-162) on n samples given explicitly (Sampling.sample_pos / sample_dir, each [n,3]; the
+ * reference ignores the sample variance too).  Outputs sdf [n], density [n], color [n,3]; d_normal (may be NULL)
+ * receives the gradient d sdf / d position [n,3] that feeds the colour trunk. */
+int32_t neddf_neus_forward(const neddf_neus_t* h, const float* d_pos, const float* d_dir, int64_t n, float* d_sdf,
+                           float* d_density, float* d_color, float* d_normal, void* stream);
+
+/* Same with the sample geometry fused (Ray.get_sampling_points / get_sampling_cones, ray.py:88-194): rays [n_rays,3],
+ * dists [n_rays, n_edges]; outputs [n_rays, n_edges] (x3 for color / normal). */
+int32_t neddf_neus_forward_rays(const neddf_neus_t* h, const float* d_ray_dir, const float* d_ray_orig, const float* d_dists,
+                                int64_t n_rays, int32_t n_edges, int32_t sampling_type, float ray_radius, float* d_sdf,
+                                float* d_density, float* d_color, float* d_normal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,14 @@ class NerfConfig(C.Structure):
     ]
 
 
+class NeusConfig(C.Structure):
+    _fields_ = [
+        ("embed_pos_rank", C.c_int32), ("embed_dir_rank", C.c_int32), ("sdf_layer_count", C.c_int32),
+        ("sdf_layer_width", C.c_int32), ("col_layer_count", C.c_int32), ("col_layer_width", C.c_int32),
+        ("activation_type", C.c_int32), ("n_skips", C.c_int32), ("skips", C.c_int32 * MAX_SKIPS),
+    ]
+
+
 class FieldState(C.Structure):
     _fields_ = [("aux_grad_scale", C.c_float), ("distance_range_max", C.c_float), ("lowpass_alpha", C.c_float),
                 ("penalty_weight", C.c_float * N_PENALTY)]
@@ -104,6 +112,12 @@ _SIGNATURES = {
     "neddf_nerf_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P]),
     "neddf_nerf_forward": (_I32, [_P, _FP, _P, _P, _P, _I64, _P, _P, _P]),
     "neddf_nerf_forward_rays": (_I32, [_P, _FP, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "neddf_neus_layer_shapes": (_I32, [C.POINTER(NeusConfig), C.POINTER(C.c_int32), _I32]),
+    "neddf_neus_create": (_I32, [C.POINTER(NeusConfig), C.POINTER(_P)]),
+    "neddf_neus_destroy": (None, [_P]),
+    "neddf_neus_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P, _P]),
+    "neddf_neus_forward": (_I32, [_P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "neddf_neus_forward_rays": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

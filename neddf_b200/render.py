@@ -22,6 +22,7 @@ from torch import Tensor, nn
 from . import _lib as L
 from .nerf import NeRF
 from .network import BaseNeuralField, NeDDF
+from .neus import NeuS
 from .ray import CONE_RAY_RADIUS, Ray
 
 _TARGET_ALIASES = {
@@ -34,6 +35,11 @@ _TARGET_ALIASES = {
     "neddf.network.nerf.NeRF": NeRF,
     "neddf_b200.NeRF": NeRF,
     "neddf_b200.nerf.NeRF": NeRF,
+    # the NeuS field variant (same item): the normal is carried forward inside the kernel, so no-grad renders work
+    "neddf.network.NeuS": NeuS,
+    "neddf.network.neus.NeuS": NeuS,
+    "neddf_b200.NeuS": NeuS,
+    "neddf_b200.neus.NeuS": NeuS,
 }
 
 
@@ -45,8 +51,8 @@ def _instantiate(network_config) -> BaseNeuralField:
     cls = _TARGET_ALIASES.get(target)
     if cls is None:
         raise NotImplementedError(
-            f"neddf_b200.NeRFRender runs the NeDDF field and the NeRF variant; network _target_={target!r} "
-            "(NeuS) is outside the B200 hot path - use the reference renderer for it")
+            f"neddf_b200.NeRFRender runs the NeDDF field and the NeRF / NeuS variants; network _target_={target!r} "
+            "is not one of them - use the reference renderer for it")
     for k in ("skips",):
         if cfg.get(k) is not None:
             cfg[k] = [int(s) for s in cfg[k]]

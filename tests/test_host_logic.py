@@ -1,4 +1,7 @@
 """CPU: host-side mirror of the reference interface (no kernels run)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -44,9 +47,56 @@ def test_cpu_tensors_are_rejected_loudly():
 
 def test_unknown_network_target_is_rejected():
     with pytest.raises(NotImplementedError):
-        neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeuS"})
+        neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.SomethingElse"})
     with pytest.raises(KeyError):
         neddf_b200.NeDDF(activation_type="gelu")
+    with pytest.raises(KeyError):  # neus.py:70-75 knows ReLU and tanhExp only
+        neddf_b200.NeuS(activation_type="LeakyReLU")
+
+
+def test_neus_module_surface_matches_the_reference():
+    """Same constructor, parameter names / shapes and initial values as neddf.network.NeuS for the same torch seed;
+    NeRFRender resolves the reference's _target_ to it; the C ABI reports the same layer shapes and refusals."""
+    import ctypes as C
+
+    from neddf_b200 import _lib as L
+    from oracle import neddf_oracle as orc
+    kw = dict(embed_pos_rank=5, embed_dir_rank=3, sdf_layer_count=6, col_layer_count=3, activation_type="tanhExp",
+              init_variance=0.45, skips=[1, 3])
+    torch.manual_seed(7)
+    net = neddf_b200.NeuS(**kw)
+    sd = net.state_dict()
+    shapes = orc.neus_layer_shapes(orc.NeusConfig(**kw))
+    assert set(sd) == {f"{n}.{p}" for n, _, _ in shapes for p in ("weight", "bias")} | {"variance"}
+    for n, cin, cout in shapes:  # torch nn.Linear keeps [out, in]
+        assert tuple(sd[n + ".weight"].shape) == (cout, cin) and tuple(sd[n + ".bias"].shape) == (cout,)
+    assert abs(float(sd["variance"]) - 0.45) < 1e-7
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):
+        sys.path.insert(0, ref_root)
+        try:
+            from neddf.network import NeuS as RefNeuS
+            torch.manual_seed(7)
+            ref = RefNeuS(**kw).state_dict()
+        finally:
+            sys.path.remove(ref_root)
+        assert list(ref) == list(sd)
+        assert all(torch.equal(ref[k], sd[k]) for k in ref)
+    r = neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeuS", **kw}, use_coarse_network=False)
+    assert isinstance(r.network_fine, neddf_b200.NeuS) and r.network_coarse is r.network_fine
+    assert len(r.get_parameters_list()) == 2 * len(shapes) + 1
+    lib = L.lib()
+    cfg = net._config_struct()
+    buf = (C.c_int32 * 64)()
+    n = lib.neddf_neus_layer_shapes(C.byref(cfg), buf, 32)
+    assert [(buf[2 * i], buf[2 * i + 1]) for i in range(n)] == [(a, b) for _, a, b in shapes]
+    bad = neddf_b200.NeuS(sdf_layer_count=4, skips=[3])._config_struct()
+    assert lib.neddf_neus_layer_shapes(C.byref(bad), None, 0) == -3 and b"skip" in lib.neddf_last_error()
+    s = neddf_b200.Sampling(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        net(s)  # CPU tensors are refused, nothing is computed on the host
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        net(s)  # autograd enabled on trainable parameters
 
 
 def test_camera_standin_matches_reference_pose():
