@@ -834,3 +834,20 @@ def neus_init_params(cfg: NeusConfig, seed: int, bias_std: float = 0.05) -> Dict
         out[name + ".bias"] = torch.randn(cout, generator=g) * bias_std
     out["variance"] = torch.tensor(float(cfg.init_variance))
     return out
+
+
+def neus_kink_distance(P: Dict[str, Tensor], cfg: NeusConfig, pos: Tensor) -> Tensor:
+    """Per sample: the smallest |pre-activation| over every unit of every SDF layer.  With ReLU the normal
+    (neus.py:133-142) is discontinuous where a pre-activation crosses zero, so two fp32 evaluations that differ in the
+    last bit may disagree there; the parity tests use this as the witness that an outlier of the normal sits on a kink."""
+    n = pos.shape[0] * pos.shape[1]
+    embed_pos = pe_plain(pos.reshape(n, 3), cfg.embed_pos_rank)
+    hx = embed_pos
+    best = torch.full((n,), float("inf"), dtype=pos.dtype)
+    for lid in range(cfg.sdf_layer_count):
+        pre = hx @ P[f"layers_sdf.{lid}.weight"] + P[f"layers_sdf.{lid}.bias"]
+        best = torch.minimum(best, pre.abs().min(dim=1).values)
+        hx = torch.relu(pre) if cfg.activation_type == "ReLU" else density_act("tanhExp", pre)
+        if lid in cfg.skips:
+            hx = torch.cat([hx, embed_pos], 1)
+    return best.reshape(pos.shape[0], pos.shape[1])

@@ -33,6 +33,27 @@ def build(c: NeusCase):
     return render, cam
 
 
+def check_normal(c: NeusCase, tag: str, pos, got, ref, what):
+    """The normal (and the colour, which reads it) against the reference at the parity bound.  With ReLU the normal is piecewise
+    constant in the hidden units' signs: a sample whose fp64 pre-activation lies within fp32 rounding of zero may
+    land on the other side in a differently ordered fp32 sum, and its normal then differs by one unit's contribution.
+    Such samples - and only such samples - are exempt: every outlier must show that witness, and there may be few
+    (tests/test_neus_oracle.py::test_relu_normal_outliers_sit_on_kinks shows the reference restatement doing the same
+    under a one-ulp shift of its inputs)."""
+    err = np.abs(got - ref).max(axis=-1) / np.abs(ref).max()
+    assert err.shape == pos.shape[:2]
+    bad = np.argwhere(err >= PARITY_TOL)
+    if c.nc.activation_type != "ReLU":
+        assert len(bad) == 0, (tag, what, float(err.max()))
+        return
+    kink = orc.neus_kink_distance(c.params(tag, torch.float64), c.nc, pos.double()).numpy()
+    report = [(tuple(int(v) for v in i), float(err[tuple(i)]), float(kink[tuple(i)])) for i in bad]
+    assert len(bad) <= max(2, err.size // 500) and float(err.max()) < 5e-2, (tag, what, report)
+    assert all(k < 5e-6 for _, _, k in report), (tag, what, "outlier away from every ReLU kink", report)
+    if report:
+        print(f"[neus normal] {tag} / {what}: {len(report)} of {err.size} samples on a ReLU kink: {report}")
+
+
 @pytest.mark.parametrize("name", ["relu", "tanhexp"])
 def test_neus_field_matches_reference(name):
     import neddf_b200
@@ -49,14 +70,16 @@ def test_neus_field_matches_reference(name):
             plain = net(neddf_b200.Sampling(pos.to(DEV), dd.contiguous().to(DEV), var.to(DEV)))
         assert sorted(plain.keys()) == ["color", "density", "sdf"]  # the reference's dictionary (neus.py:155-160)
         assert torch.equal(plain["color"], out["color"])
-        for k in ("sdf", "density", "color"):
+        for k in ("sdf", "density"):  # continuous across the ReLU kinks: strict bound
             ref = c.z[f"field_{tag}_{k}"]
             assert out[k].shape == ref.shape
             assert nerr(out[k].cpu().numpy(), ref) < PARITY_TOL, (tag, k)
             assert nerr(fused[k].cpu().numpy(), ref) < PARITY_TOL, (tag, k, "fused geometry")
+        for what, got in (("explicit samples", out["color"]), ("fused geometry", fused["color"])):
+            check_normal(c, tag, pos, got.cpu().numpy(), c.z[f"field_{tag}_color"], "color, " + what)
         grad = orc.neus_forward(c.params(tag), c.nc, pos, dd)["gradients"].numpy()  # torch.autograd.grad, neus.py:133-142
-        assert nerr(out["normal"].cpu().numpy(), grad) < PARITY_TOL, (tag, "normal")
-        assert nerr(fused["normal"].cpu().numpy(), grad) < PARITY_TOL, (tag, "normal", "fused geometry")
+        for what, got in (("explicit samples", out["normal"]), ("fused geometry", fused["normal"])):
+            check_normal(c, tag, pos, got.cpu().numpy(), grad, what)
 
 
 @pytest.mark.parametrize("name", ["relu", "tanhexp"])

@@ -73,3 +73,28 @@ def test_neus_forward_mode_equals_autograd_in_fp64():
         a, b = orc.neus_forward(P, cfg, pos, dd), orc.neus_forward_jac(P, cfg, pos, dd)
         for k in a:
             assert float((a[k] - b[k]).abs().max()) < 1e-12, (act, k)
+
+
+def test_relu_normal_outliers_sit_on_kinks():
+    """Why the GPU test of the normal exempts a few ReLU samples.  The reference restatement itself, in fp32, fed
+    positions shifted by ONE ulp: sdf, density and colour move by 1e-6, but the normal of a few samples moves by
+    1e-4 .. 1e-3 - exactly the samples where the fp64 run has a hidden pre-activation within rounding distance of
+    zero (the ReLU slope, hence the reverse-mode gradient of neus.py:133-142, flips).  Smooth tanhExp: none."""
+    for name, expect_outliers in (("relu", True), ("tanhexp", False)):
+        c = NeusCase(name)
+        d, o = orc.make_rays(c.t("uv"), c.cam)
+        pos, dd, _ = orc.make_samples(c.rc, d, o, c.t("dists_fine"))
+        P = c.params("fine")
+        base = orc.neus_forward(P, c.nc, pos, dd)
+        kink = orc.neus_kink_distance(c.params("fine", torch.float64), c.nc, pos.double()).numpy()
+        n_out = 0
+        for sign in (1.0, -1.0):
+            moved = orc.neus_forward(P, c.nc, torch.nextafter(pos, torch.full_like(pos, sign * float("inf"))), dd)
+            for k in ("sdf", "density", "color"):
+                assert nerr(moved[k].numpy(), base[k].numpy()) < 1e-5, (name, k)
+            err = (moved["gradients"] - base["gradients"]).abs().amax(-1).numpy() / float(base["gradients"].abs().max())
+            bad = np.argwhere(err >= 1e-4)
+            n_out += len(bad)
+            assert len(bad) <= max(2, err.size // 500) and float(err.max()) < 5e-2
+            assert all(kink[tuple(i)] < 5e-6 for i in bad), [(tuple(i), err[tuple(i)], kink[tuple(i)]) for i in bad]
+        assert (n_out > 0) == expect_outliers, (name, n_out)
