@@ -283,7 +283,7 @@ def test_errors_are_loud():
         with torch.no_grad():
             render.render_rays(c.t("uv").to(G.DEV), cam, uniforms=(torch.rand(3, 65), torch.rand(3, 129)))
     with pytest.raises(NotImplementedError):
-        neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeRF"})
+        neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.SomethingElse"})  # NeDDF, NeRF, NeuS are served
 
 
 def _bench_render(engine):
