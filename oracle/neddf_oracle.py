@@ -314,6 +314,8 @@ def field_forward(
     h, hJ = es, Jes
     for lid in range(cfg.ddf_layer_count - 1):
         h, hJ = linear_jac(h, hJ, P[f"layers_ddf.{lid}.weight"], P[f"layers_ddf.{lid}.bias"], mm)
+        if taps is not None:
+            taps[f"ddf{lid}_pre"] = h
         h, hJ = act(h, hJ)
         if taps is not None:
             taps[f"ddf{lid}_x"], taps[f"ddf{lid}_J"] = h, hJ
@@ -343,6 +345,8 @@ def field_forward(
     cJ = torch.cat([Je0, torch.zeros(n, 3, ed.shape[1] + 3, dtype=dt), hJ], 2)
     for lid in range(cfg.col_layer_count - 1):
         c, cJ = linear_jac(c, cJ, P[f"layers_col.{lid}.weight"], P[f"layers_col.{lid}.bias"], mm)
+        if taps is not None:
+            taps[f"col{lid}_pre"] = c
         c, cJ = act(c, cJ)
         if taps is not None:
             taps[f"col{lid}_x"], taps[f"col{lid}_J"] = c, cJ
