@@ -427,6 +427,9 @@ class NeRFRender(BaseNeuralRender):
         target_types = list(target_types)
         lib = L.lib()
         device = torch.device(device) if device is not None else self.network_fine.device
+        if device.type != "cuda":
+            raise RuntimeError(f"neddf_b200.NeRFRender renders on CUDA devices only (the module is on {device}): move it "
+                               "with .to('cuda') - the hot path has no CPU implementation")
         hR, hT, hC = _camera_host(camera)
         outs: Dict[str, List[Tensor]] = {k: [] for k in target_types}
         with torch.no_grad(), torch.cuda.device(device):

@@ -399,13 +399,29 @@ def test_voxelize_and_field_slice():
     assert fields["distance"].shape == (32, 32, 3) and fields["distance"].dtype == np.uint8
     assert fields["color"].shape == (32, 32, 3)
     assert render.network_fine.training  # module mode untouched
+    # values: the oracle on the same grid through the reference's scale table and colour map (nerf_render.py:295-334)
+    import cv2
+    lin = torch.linspace(-1.1, 1.1, 32)
+    gx, gy = lin.reshape(1, -1).expand(32, 32), -lin.reshape(-1, 1).expand(32, 32)
+    gpos = torch.stack([gx, gy, torch.zeros(32, 32)], 2).contiguous()
+    gdir = torch.zeros_like(gpos)
+    gdir[:, :, 2] = 1.0
+    ref = orc.field_forward(c.p_fine, c.fc, c.st, gpos, gdir, torch.zeros_like(gpos))
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), cv2.COLORMAP_JET).reshape(256, 3).astype(np.int32)
+    for key, scale in (("distance", 256.0), ("density", 12.8), ("color", 256.0), ("aux_grad", 256.0)):
+        level = (scale * ref[key].reshape(32, 32, -1)).numpy().clip(0, 255).astype(np.uint8)
+        got = fields[key]
+        if level.shape[2] == 1:  # colour-mapped scalar field: recover the 8-bit level from the JET table
+            got = np.abs(got.astype(np.int32)[:, :, None, :] - lut[None, None]).sum(-1).argmin(-1)[:, :, None]
+        diff = np.abs(got.astype(np.int32) - level.astype(np.int32))
+        assert diff.max() <= 1 and (diff == 0).mean() > 0.97, (key, int(diff.max()), float((diff == 0).mean()))
 
 
 @pytest.mark.parametrize("engine", ENGINES)
 def test_training_state_forward_values(engine):
     """Warm-up scalars of NeDDF.set_iter(3000) (aux_grad_scale 0.3, neddf.py:323-326): forward
-    values against the reference's grad-mode run (golden case_train); the backward itself is not
-    built yet, so the call is made under no_grad."""
+    values against the reference's grad-mode run (golden case_train), forward only (the gradients of the same
+    case are held to the reference's by test_render_rays_training_matches_reference_gradients)."""
     G = _gpu()
     c = Case("train")
     render, cam = G.build_render(c, engine), G.build_camera(c)
