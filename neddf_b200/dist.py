@@ -7,10 +7,13 @@ into ``world_size`` contiguous slices, each rank renders its slice with the sing
 kernels, and the only communication is ONE all-gather per frame of the packed
 [pixels/rank, C] fp32 tile (NCCL over NVLink; gloo on CPU for the host-logic tests).
 """
+import warnings
 from typing import Dict, Iterable, List, Tuple
 
 import torch
 import torch.distributed as dist
+
+from .network import EngineRangeError
 
 
 def shard_range(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -68,7 +71,12 @@ def render_image_sharded(render, width: int, height: int, camera, target_types: 
         u = (uniforms[0][first:first + count], uniforms[1][first:first + count])
     flat = render.render_pixels(width, height, camera, target_types, downsampling, first, count, u)
     if getattr(render, "check_nan", False):
-        render.check_status()  # NaN weights raise, a failed resampling is reported - like render_image
+        try:
+            render.check_status()  # NaN weights raise, a failed resampling is reported - like render_image
+        except EngineRangeError as e:  # engine "auto" left fp16 range on this rank: its shard again on the fp32 engine
+            warnings.warn(str(e), RuntimeWarning)
+            flat = render.render_pixels(width, height, camera, target_types, downsampling, first, count, u)
+            render.check_status()
     widths = [flat[k].shape[1] for k in target_types]
     packed = torch.cat([flat[k] for k in target_types], 1) if len(target_types) > 1 else flat[target_types[0]]
     full = gather_tiles(packed, n_pix, group)

@@ -75,11 +75,11 @@ class _FieldTrainFn(torch.autograd.Function):
                 L.check(L.lib().neddf_field_forward_train(
                     h, C.byref(st), L.ptr(a), L.ptr(b), L.ptr(c), B, S, L.SAMPLING_IDS[sampling_type],
                     float(ray_radius), L.ptr(density), L.ptr(color), L.ptr(penalty), L.ptr(save),
-                    L.ENGINE_IDS[net.engine], L.stream_ptr(device)), "field_forward_train")
+                    net._engine_id(), L.stream_ptr(device)), "field_forward_train")
             else:
                 L.check(L.lib().neddf_field_forward_train_samples(
                     h, C.byref(st), L.ptr(a), L.ptr(b), L.ptr(c), n, L.ptr(distance), L.ptr(density), L.ptr(color),
-                    L.ptr(penalty), L.ptr(aux), L.ptr(save), L.ENGINE_IDS[net.engine], L.stream_ptr(device)),
+                    L.ptr(penalty), L.ptr(aux), L.ptr(save), net._engine_id(), L.stream_ptr(device)),
                     "field_forward_train_samples")
         ctx.net = net
         ctx.meta = (sampling_type, float(ray_radius),
@@ -182,6 +182,11 @@ class _FieldTrainFn(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(grads)
 
 
+class EngineRangeError(FloatingPointError):
+    """The tensor-core engine left fp16 range under engine "auto"; the network has switched itself to the fp32 engine
+    and the caller (NeRFRender) re-runs the call.  Explicit engines ("tc", "tc2") raise plain FloatingPointError."""
+
+
 class BaseNeuralField(nn.Module):
     """neddf/network/base_neuralfield.py:11-79."""
 
@@ -269,6 +274,7 @@ class NeDDF(BaseNeuralField):
 
         # kernel-side state
         self.engine = "auto"          # "auto" | "fp32" | "tc" | "tc2"
+        self._range_fallback = False  # "auto" met an activation outside fp16 range: it resolves to fp32 from then on
         self._handle = None
         self._handle_device = None
         self._packed_key = None
@@ -277,8 +283,13 @@ class NeDDF(BaseNeuralField):
     def resolved_engine(self, device=None) -> str:
         """Engine that will actually run for ``self.engine`` ("fp32" or "tc")."""
         h = self._field(torch.device(device) if device is not None else self.device)
-        rc = L.check(L.lib().neddf_field_resolve_engine(h, L.ENGINE_IDS[self.engine]), "resolve_engine")
+        rc = L.check(L.lib().neddf_field_resolve_engine(h, self._engine_id()), "resolve_engine")
         return {1: "fp32", 2: "tc", 3: "tc2"}[rc]
+
+    def _engine_id(self) -> int:
+        """ABI engine id of the next launch: ``self.engine``, except that "auto" stays on the fp32 engine once the
+        tensor-core engine has reported an activation outside fp16 range for this network (check_engine_status)."""
+        return L.ENGINE_IDS["fp32" if (self._range_fallback and self.engine == "auto") else self.engine]
 
     # ------------------------------------------------------------------ kernel plumbing --
     def _ordered_layers(self) -> List[LinearGradLayer]:
@@ -413,7 +424,7 @@ class NeDDF(BaseNeuralField):
             L.check(L.lib().neddf_field_forward(
                 h, C.byref(st), L.ptr(p3), L.ptr(d3), L.ptr(v3), n, L.ptr(out["distance"]), L.ptr(out["density"]),
                 L.ptr(out["color"]), L.ptr(out["fields_penalty"]), L.ptr(out["aux_grad"]), L.OUT_FULL,
-                L.ENGINE_IDS[self.engine], L.stream_ptr(device)), "field_forward")
+                self._engine_id(), L.stream_ptr(device)), "field_forward")
         return out
 
     def forward_rays(self, ray_dir: Tensor, ray_orig: Tensor, dists: Tensor, sampling_type: str, ray_radius: float,
@@ -453,7 +464,7 @@ class NeDDF(BaseNeuralField):
                 h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, S, L.SAMPLING_IDS[sampling_type],
                 float(ray_radius), L.ptr(out.get("distance")), L.ptr(out["density"]), L.ptr(out["color"]),
                 L.ptr(out.get("fields_penalty")), L.ptr(out.get("aux_grad")),
-                L.OUT_FULL if need_penalty else L.OUT_EVAL, L.ENGINE_IDS[self.engine], L.stream_ptr(device)),
+                L.OUT_FULL if need_penalty else L.OUT_EVAL, self._engine_id(), L.stream_ptr(device)),
                 "field_forward_rays")
         if prof is not None:
             e1.record(torch.cuda.current_stream(device))
@@ -478,7 +489,7 @@ class NeDDF(BaseNeuralField):
             L.check(L.lib().neddf_field_forward_rays_segment(
                 h, C.byref(st), L.ptr(ray_dir), L.ptr(ray_orig), L.ptr(dists), B, E, L.SAMPLING_IDS[sampling_type],
                 float(ray_radius), int(edge0), int(seg_len), L.ptr(ray_index), L.ptr(n_active), L.ptr(density),
-                L.ptr(color), L.ENGINE_IDS[self.engine], L.stream_ptr(device)), "field_forward_rays_segment")
+                L.ptr(color), self._engine_id(), L.stream_ptr(device)), "field_forward_rays_segment")
         if prof is not None:
             e1.record(torch.cuda.current_stream(device))
             prof.append((e0, e1, None))  # the executed count lives on the device (NeRFRender.termination_stats)
@@ -493,9 +504,14 @@ class NeDDF(BaseNeuralField):
         with torch.cuda.device(dev):
             L.check(L.lib().neddf_field_status(self._handle, C.byref(v), L.stream_ptr(dev)), "field_status")
         if v.value & 4:
+            if self.engine == "auto" and not self._range_fallback:
+                self._range_fallback = True
+                raise EngineRangeError(
+                    "neddf_b200: tensor-core engine saw |activation| > 65504 (fp16 range of its split operands); "
+                    "engine 'auto' now resolves to the fp32 engine for this network and the call is re-run")
             raise FloatingPointError(
                 "neddf_b200: tensor-core engine saw |activation| > 65504 (fp16 range of its split operands); "
-                "results of the last calls are invalid - use set_engine('fp32') for this network")
+                "results of the last calls are invalid - use set_engine('fp32') or 'auto' for this network")
 
     def set_iter(self, iter: int) -> None:
         """Warm-up schedule (neddf.py:311-326); -1 = evaluation."""

@@ -13,6 +13,7 @@ comparable with the reference fed the same numbers.
 """
 import importlib
 import math
+import warnings
 from typing import Any, Dict, Iterable, List, Optional, Tuple
 
 import numpy as np
@@ -21,7 +22,7 @@ from torch import Tensor, nn
 
 from . import _lib as L
 from .nerf import NeRF
-from .network import BaseNeuralField, NeDDF
+from .network import BaseNeuralField, EngineRangeError, NeDDF
 from .neus import NeuS
 from .ray import CONE_RAY_RADIUS, Ray
 
@@ -221,11 +222,19 @@ class BaseNeuralRender(nn.Module):
         """The reference asserts `not any(isnan(w))` inside integrate_volume_render
         (base_neural_render.py:155) - a host sync per call.  The kernels record the condition in
         a device flag instead; this reads it (one sync) and raises like the reference."""
+        range_error = None
         for net in {id(n): n for n in (getattr(self, "network_coarse", None), getattr(self, "network_fine", None))
                     if n is not None}.values():
             if hasattr(net, "check_engine_status"):
-                net.check_engine_status()
+                try:
+                    net.check_engine_status()
+                except EngineRangeError as e:  # keep going: the other network's flag must be read (and cleared) too
+                    range_error = e
         st = getattr(self, "_status_buf", None)
+        if range_error is not None:
+            if st is not None:
+                st.zero_()  # flags of the invalid run
+            raise range_error
         if st is None:
             return
         v = int(st[0].item())
@@ -295,8 +304,10 @@ class NeRFRender(BaseNeuralRender):
         """"auto" | "fp32" (CUDA-core fp32 FMA) | "tc" (tcgen05, split-fp16 operands)."""
         if engine not in L.ENGINE_IDS:
             raise ValueError(engine)
-        self.network_fine.engine = engine
-        self.network_coarse.engine = engine
+        for net in (self.network_fine, self.network_coarse):
+            net.engine = engine
+            if hasattr(net, "_range_fallback"):
+                net._range_fallback = False  # an explicit choice starts afresh
 
     @property
     def _ray_radius(self) -> float:
@@ -401,8 +412,14 @@ class NeRFRender(BaseNeuralRender):
                                             L.ptr(ray_orig), L.stream_ptr(device)), "make_rays")
             u_c, u_f = self._uniforms(B, device, uniforms)
             out = self._render_core(ray_dir, ray_orig, u_c, u_f, full=True)
-        if self.check_nan:
-            self.check_status()
+            if self.check_nan:
+                try:
+                    self.check_status()
+                except EngineRangeError as e:  # engine "auto" left fp16 range: same rays, same uniforms, fp32 engine
+                    warnings.warn(str(e), RuntimeWarning)
+                    out = None  # release the invalid run (under autograd: its saved activations) before the second one
+                    out = self._render_core(ray_dir, ray_orig, u_c, u_f, full=True)
+                    self.check_status()
         return out
 
     def create_rays(self, uv: Tensor, camera) -> Ray:
@@ -468,7 +485,13 @@ class NeRFRender(BaseNeuralRender):
             self.network_fine.train(True)
         del was_training
         if self.check_nan:
-            self.check_status()
+            try:
+                self.check_status()
+            except EngineRangeError as e:  # engine "auto" left fp16 range: render the frame again on the fp32 engine
+                warnings.warn(str(e), RuntimeWarning)
+                with torch.no_grad():
+                    flat = self.render_pixels(width, height, camera, target_types, downsampling, 0, w * h, uniforms)
+                self.check_status()
         return {k: v.reshape(h, w, -1) for k, v in flat.items()}
 
     def render_field_slice(self, slice_t: float = 0.0, render_size: float = 1.1,

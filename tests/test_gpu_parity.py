@@ -898,3 +898,42 @@ def test_tc_batched_colour_trunk_matches_per_tile_program(case, n_rays, monkeypa
             assert int((e >= PARITY_TOL).sum()) <= max(2, int(1e-2 * e.size)) and e.max() < 5e-2, (k, e.max())
         else:
             assert e.max() < PARITY_TOL, (k, e.max())
+
+
+def test_auto_engine_leaves_fp16_range_gracefully():
+    """Engine cliff: weights that push a hidden activation beyond fp16 range (65504, the
+    limit of the tensor-core engine's split operands).  Explicit "tc" / "tc2" raise; "auto" switches the network to
+    the fp32 engine, warns and re-runs the call - same rays, same uniforms - so the result is the fp32 engine's, bit
+    for bit, and later calls stay there without another detour."""
+    G = _gpu()
+    c = Case("bunny")
+    render, cam = G.build_render(c, "auto"), G.build_camera(c)
+    with torch.no_grad():
+        render.network_fine.layers_col[0].weight.mul_(1e5)  # colour trunk only: densities / weights stay sane
+    uv = c.t("uv").to(G.DEV)
+    u = (c.t("u_coarse").to(G.DEV), c.t("u_fine").to(G.DEV))
+    assert render.network_fine.resolved_engine() == "tc"
+    with torch.no_grad():
+        with pytest.warns(RuntimeWarning, match="fp16 range"):
+            out = render.render_rays(uv, cam, uniforms=u)
+        assert render.network_fine.resolved_engine() == "fp32"
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("error", RuntimeWarning)  # no second detour
+            again = render.render_rays(uv, cam, uniforms=u)
+            img = render.render_image(40, 30, cam, ["color", "depth"], 1, 512)
+        render.set_engine("fp32")
+        ref = render.render_rays(uv, cam, uniforms=u)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]) and torch.equal(again[k], ref[k]), k
+        assert bool(torch.isfinite(ref["color"]).all()) and bool(torch.isfinite(img["color"]).all())
+        assert float(ref["color"].abs().max()) > 1e3  # the blown-up colour trunk really is out of fp16 territory
+        for engine in ("tc", "tc2"):
+            render.set_engine(engine)
+            with pytest.raises(FloatingPointError, match="65504"):
+                render.render_rays(uv, cam, uniforms=u)
+        # the image path of a fresh "auto" renderer takes the same detour once
+        render.set_engine("auto")
+        with pytest.warns(RuntimeWarning, match="fp16 range"):
+            img2 = render.render_image(40, 30, cam, ["color", "depth"], 1, 512)
+        assert bool(torch.isfinite(img2["color"]).all()) and render.network_fine.resolved_engine() == "fp32"
