@@ -13,6 +13,10 @@ the build container by ``tests/golden/make_golden.py`` (which imports
 ``/root/reference`` and records inputs/outputs into ``tests/golden/*.npz``), by
 ``tests/test_oracle_golden.py``.
 
+The NeRF and NeuS field variants (end of this file) are pinned the same way: ``make_nerf_golden.py`` /
+``make_neus_golden.py`` run the reference's own networks inside its NeRFRender, ``tests/test_nerf_oracle.py`` /
+``tests/test_neus_oracle.py`` hold ``nerf_forward`` / ``neus_forward`` to 2e-6 of them.
+
 Every function cites the reference file:line it restates (paths relative to the
 reference root).  All tensors are [rays, samples, ...] row-major; ``dtype`` may be
 float32 (parity target) or float64 (arbiter for ill-conditioned samples).

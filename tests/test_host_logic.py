@@ -276,3 +276,54 @@ def test_eval_io_writer_matches_the_reference_tail(tmp_path):
         assert np.array_equal(cv2.imread(str(tmp_path / f"{i:03}_rgb_gt.png")), gts[i])
         mse = np.mean((rgb_ref.astype(np.float64) - gts[i].astype(np.float64)) ** 2)
         assert abs(eval_io.psnr_uint8(rgb_ref, gts[i]) - 10 * np.log10(255.0 ** 2 / mse)) < 1e-12
+
+
+def test_engine_range_fallback_host_logic(monkeypatch):
+    """Engine "auto" leaving fp16 range (status bit 4 of neddf_field_status): the network marks itself and raises
+    EngineRangeError once, the renderer reads BOTH networks' flags, clears its own NaN flags of the invalid run and
+    re-raises; explicit engines raise plain FloatingPointError; set_engine starts afresh.  (The device side and the
+    re-run are covered by tests/test_gpu_parity.py::test_auto_engine_leaves_fp16_range_gracefully.)"""
+    import ctypes as C
+
+    from neddf_b200 import _lib as L
+    from neddf_b200.network import EngineRangeError
+
+    class FakeLib:
+        def __init__(self):
+            self.status = {}
+
+        def neddf_field_status(self, handle, out, stream):
+            out._obj.value = self.status.pop(handle.value, 0)  # read-and-clear, like the kernel-side word
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(L, "lib", lambda: fake)
+    monkeypatch.setattr(L, "stream_ptr", lambda device=None: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: __import__("contextlib").nullcontext())
+    r = neddf_b200.NeRFRender(network_config={"_target_": "neddf.network.NeDDF"}, use_coarse_network=True)
+    for i, net in enumerate((r.network_coarse, r.network_fine)):
+        net._handle, net._handle_device = C.c_void_p(100 + i), torch.device("cpu")
+        monkeypatch.setattr(net, "_release", lambda: None)
+    r._status_buf = torch.tensor([1, 0], dtype=torch.int32)  # a NaN flag left by the invalid run
+    fake.status = {100: 4, 101: 4}
+    with pytest.raises(EngineRangeError):
+        r.check_status()
+    assert fake.status == {}  # both words were read although the first network already raised
+    assert r.network_coarse._range_fallback and r.network_fine._range_fallback
+    assert int(r._status_buf[0]) == 0  # flags of the invalid run are gone: the re-run starts clean
+    assert r.network_fine._engine_id() == L.ENGINE_IDS["fp32"]
+    r.check_status()  # nothing pending any more
+    fake.status = {101: 4}  # still out of range although already on fp32?  that is an error, not another detour
+    with pytest.raises(FloatingPointError) as ei:
+        r.check_status()
+    assert not isinstance(ei.value, EngineRangeError)
+    r.set_engine("tc")
+    assert not r.network_fine._range_fallback and r.network_fine._engine_id() == L.ENGINE_IDS["tc"]
+    fake.status = {100: 4}
+    with pytest.raises(FloatingPointError) as ei:
+        r.check_status()
+    assert not isinstance(ei.value, EngineRangeError)
+    r.set_engine("auto")
+    assert r.network_fine._engine_id() == L.ENGINE_IDS["auto"]
+    for net in (r.network_coarse, r.network_fine):
+        net._handle = None

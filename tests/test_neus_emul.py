@@ -51,9 +51,10 @@ def _cfg_struct(nc: orc.NeusConfig):
     return c
 
 
-def run_emul(lib, c: NeusCase, tag: str, pos=None, dirs=None, rays=None, nblocks=2):
+def run_emul(lib, c, tag: str, pos=None, dirs=None, rays=None, nblocks=2):
     """The emulated kernel on explicit samples (pos, dirs [n,3]) or rays ((ray_dir, ray_orig, dists), fused geometry);
-    weights in torch's own [out,in] layout, straight from the reference's state_dict."""
+    weights in torch's own [out,in] layout, straight from the reference's state_dict (``c`` = a NeusCase, or any
+    object with ``nc``, ``rc`` and a dict ``z`` of ``w_fine.<state_dict key>`` arrays)."""
     pre = f"w_{tag}." if f"w_{tag}.layers_sdf.0.weight" in c.z else "w_fine."
     names = [n for n, _, _ in orc.neus_layer_shapes(c.nc)]
     ws = [np.ascontiguousarray(c.z[pre + n + ".weight"], dtype=np.float32) for n in names]
@@ -118,3 +119,33 @@ def test_emulated_kernel_refuses_what_the_abi_refuses(emul):
     cfg = _cfg_struct(bad)
     assert emul.neus_emul_forward(C.byref(cfg), None, None, 0, None, None, None, None, None, None, C.c_longlong(0), 0, 0,
                                   C.c_float(0.0), None, None, None, None, 1) == -1
+
+
+class _Synthetic:
+    """Seeded weights for configurations the goldens do not cover (stored like a golden: torch's [out,in])."""
+
+    def __init__(self, nc: orc.NeusConfig, seed: int):
+        self.nc, self.rc = nc, orc.RenderConfig(sampling_type="point")
+        self.P = orc.neus_init_params(nc, seed)
+        self.z = {"w_fine." + k: (v.t().contiguous().numpy() if k.endswith(".weight") else v.numpy()) for k, v in self.P.items()}
+
+
+@pytest.mark.parametrize("kw", [
+    # largest embeddings the kernel accepts (60 + 30 rows), shallowest trunks, a skip right after the first layer
+    dict(embed_pos_rank=10, embed_dir_rank=4, sdf_layer_count=2, col_layer_count=1, activation_type="tanhExp", skips=[0]),
+    # one SDF layer (sdf = channel 0 of the first layer), no skip at all, smallest embeddings
+    dict(embed_pos_rank=1, embed_dir_rank=1, sdf_layer_count=1, col_layer_count=2, activation_type="ReLU", skips=[]),
+], ids=["max-embeddings-skip0", "one-sdf-layer"])
+def test_emulated_kernel_layer_table_extremes(emul, kw):
+    """Configurations at the edges of what neddf_neus_create accepts, against the oracle (70 samples: one full tile
+    and a ragged one whose last SDF sub-tile is partly empty)."""
+    c = _Synthetic(orc.NeusConfig(**kw), seed=5)
+    g = torch.Generator().manual_seed(9)
+    pos = torch.rand(1, 70, 3, generator=g) * 2 - 1
+    dd = torch.nn.functional.normalize(torch.randn(1, 70, 3, generator=g), dim=-1)
+    got = run_emul(emul, c, "fine", pos=pos, dirs=dd, nblocks=2)
+    ref = orc.neus_forward(c.P, c.nc, pos, dd)
+    for k, rk in (("sdf", "sdf"), ("density", "density"), ("color", "color"), ("normal", "gradients")):
+        r = ref[rk].numpy()
+        assert np.isfinite(got[k]).all(), k
+        assert np.abs(got[k] - r).max() <= 2e-5 * max(np.abs(r).max(), 1.0), (k, float(np.abs(got[k] - r).max()))
