@@ -32,4 +32,57 @@ def compose(config_name="config", overrides=()):
     return cfg
 
 
-__all__ = ["initialize_config_dir", "compose", "utils", "DictConfig", "ListConfig"]
+def _compose_tree(config_dir, config_name, overrides):
+    """config.yaml with a defaults list of `group: option` entries (config/config.yaml of the reference), group
+    overrides `group=option` and value overrides `a.b=value`."""
+    with open(os.path.join(config_dir, config_name + ".yaml")) as f:
+        root = yaml.safe_load(f) or {}
+    defaults = root.pop("defaults", [])
+    choices = {}
+    for d in defaults:
+        if isinstance(d, dict):
+            choices.update(d)
+    value_ov = []
+    for ov in overrides:
+        key, _, val = ov.partition("=")
+        if key in choices and "." not in key:
+            choices[key] = val
+        else:
+            value_ov.append((key, val))
+    cfg = OmegaConf.create(root)
+    for group, option in choices.items():
+        with open(os.path.join(config_dir, group, str(option) + ".yaml")) as f:
+            cfg[group] = yaml.safe_load(f)
+    for key, val in value_ov:
+        OmegaConf.update(cfg, key, yaml.safe_load(val))
+    return cfg
+
+
+def main(config_path=None, config_name="config", version_base=None):
+    """@hydra.main: compose the config tree next to the decorated function's file, apply the command-line overrides,
+    run the task from a fresh working directory (hydra.run.dir; here NEDDF_HARNESS_RUN_DIR or a temp dir)."""
+    import functools
+    import inspect
+    import sys
+    import tempfile
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper():
+            src_dir = os.path.dirname(os.path.abspath(inspect.getsourcefile(fn)))
+            config_dir = os.path.normpath(os.path.join(src_dir, config_path))
+            extra = [o for o in os.environ.get("NEDDF_HARNESS_OVERRIDES", "").split(",") if o]
+            cfg = _compose_tree(config_dir, config_name, [a for a in sys.argv[1:] if "=" in a] + extra)
+            utils._original_cwd = os.getcwd()
+            run_dir = os.environ.get("NEDDF_HARNESS_RUN_DIR") or tempfile.mkdtemp(prefix="hydra_run_")
+            os.makedirs(run_dir, exist_ok=True)
+            os.chdir(run_dir)
+            try:
+                return fn(cfg)
+            finally:
+                os.chdir(utils._original_cwd)
+        return wrapper
+    return deco
+
+
+__all__ = ["initialize_config_dir", "compose", "main", "utils", "DictConfig", "ListConfig"]

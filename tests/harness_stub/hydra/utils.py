@@ -3,6 +3,14 @@ import importlib
 from omegaconf import DictConfig, ListConfig
 
 
+_original_cwd = None
+
+
+def get_original_cwd():
+    assert _original_cwd is not None, "only valid inside a @hydra.main task"
+    return _original_cwd
+
+
 def _locate(target: str):
     mod, _, name = target.rpartition(".")
     return getattr(importlib.import_module(mod), name)  # attribute lookup at call time, like hydra's _locate

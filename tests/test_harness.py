@@ -45,6 +45,34 @@ def test_run_eval_reaches_the_kernel_boundary(tmp_path):
     assert (run_dir / "eval").is_dir()  # run_eval.py:41-42 created its output directory before rendering
 
 
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "data", "bunny_smoke")), reason="needs /root/reference")
+@pytest.mark.parametrize("argv,patch", [
+    ([], "0"),                                                                                    # config/config.yaml defaults: NeDDF
+    (["network=nerf", "render=nerf_render", "loss=nerf_loss", "trainer=nerf_trainer"], "1"),  # NeRF groups + trainer glue
+], ids=["neddf-defaults", "nerf-groups-patched-trainer"])
+def test_run_train_reaches_the_kernel_boundary(tmp_path, argv, patch):
+    """The reference's TRAINING entry point, unmodified (`neddf/scripts/run.py`, @hydra.main over config/config.yaml
+    with its defaults list): dataset, cameras, loss modules, NeRFTrainer, Adam, `run_train` -> `run_train_step` ->
+    `neural_render.render_rays(uv, camera)` on the B200 class, which refuses the CPU tensors loudly.  With
+    NEDDF_B200_PATCH_TRAINER=1 the launcher also rebinds the loss classes / ground-truth gather / render_all that
+    Hydra then instantiates from the `loss` group."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU harness: on a GPU box this would start a 2000-epoch training run")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "harness_stub"), REF, REPO])
+    env["NEDDF_HARNESS_OVERRIDES"] = "trainer.device=cpu"
+    env["NEDDF_HARNESS_RUN_DIR"] = str(tmp_path / "run")
+    env["NEDDF_B200_PATCH_TRAINER"] = patch
+    r = subprocess.run([sys.executable, os.path.join(HERE, "harness_stub", "run_cpu.py"), "neddf/scripts/run.py"] + argv,
+                       cwd=REF, env=env, capture_output=True, text=True, timeout=900)
+    log = r.stdout + r.stderr
+    assert r.returncode != 0, log[-2000:]
+    assert "epoch:  0" in r.stdout, log[-2000:]                                   # nerf_trainer.py:58
+    assert "nerf_trainer.py" in r.stderr and "run_train_step" in r.stderr, log[-2000:]
+    assert "neddf_b200/render.py" in r.stderr and "must live on the CUDA device" in r.stderr, log[-2000:]
+    assert (tmp_path / "run" / "models").is_dir()                                 # nerf_trainer.py:52, in hydra's run dir
+
+
 def test_constructors_accept_hydra_config_nodes():
     """`_recursive_=False` hands NeRFRender the network node as a DictConfig whose `skips` / `penalty_weight` are
     ListConfig / DictConfig (not list / dict); the render node's scalars arrive as keyword arguments."""
