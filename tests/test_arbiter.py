@@ -71,3 +71,34 @@ def test_kinked_outliers_sit_on_kinks():
         outliers[name] = n_bad
     assert outliers["bunny"] == 0, outliers  # smooth activation: no exemption needed, none granted (Case.kinked is False)
     assert outliers["leaky"] > 0, outliers   # measured: 3 of 1552 samples, kink distances <= 2.4e-6
+
+
+def test_reference_gradients_against_the_fp64_arbiter():
+    """Gradient parity budget.  The gradients the REAL reference's hand-written backward
+    produced in fp32 (golden case_train, 26 tensors, loss over both passes) against the oracle's fp64 autograd run of
+    the same step: the reference itself sits at ~2.4e-6 of the exact gradients, the fp32 restatement at the same
+    distance and at 6e-7 of the reference.  The CUDA training path is measured at 1.6e-6 .. 3.5e-5 of fp64
+    (tools/grad_err.py, profiles/r02_summary.md section 5) - inside the 1e-4 the GPU tests assert
+    (test_field_backward_matches_autograd; 2e-4 end to end through the resampling)."""
+    c = Case("train")
+
+    def grads(dtype):
+        p = {k: v.clone().to(dtype).requires_grad_(True) for k, v in c.p_fine.items()}
+        out = orc.render_rays(p, p, c.fc, c.st, c.rc, c.t("uv"), c.cam, c.t("u_coarse"), c.t("u_fine"), dtype=dtype)
+        loss = (out["color"].sum() + 0.1 * out["depth"].sum() + 0.05 * out["transmittance"].sum()
+                + 0.01 * out["fields_penalty"].sum() + 0.1 * out["color_coarse"].sum()
+                + 0.001 * out["fields_penalty_coarse"].sum())  # the loss of tests/golden/make_golden.py
+        loss.backward()
+        return {k: v.grad.numpy() for k, v in p.items()}
+
+    g64, g32 = grads(torch.float64), grads(torch.float32)
+    worst_ref, worst_32 = 0.0, 0.0
+    for k, exact in g64.items():
+        ref = c.z["grad_network_fine." + k]
+        a, b = exact, g32[k]
+        if a.ndim == 2 and a.shape[1] > 3:  # the fixture keeps every 8th input row of the big matrices
+            a, b = a[::8], b[::8]
+        worst_ref = max(worst_ref, nerr(ref, a))
+        worst_32 = max(worst_32, nerr(b, a))
+    assert worst_ref < 2e-5 and worst_32 < 2e-5, (worst_ref, worst_32)  # measured 2.4e-6 / 2.5e-6
+    assert worst_ref > 1e-7  # and not zero: fp32 has a floor, the 1e-4 bar leaves it a factor ~40
