@@ -27,7 +27,14 @@ namespace {
 struct HostCtx {
   int tid, block, nblocks;
   pthread_barrier_t* bar;
+#ifdef NEUS_EMUL_DROP_BARRIER  // negative control of the sanitizer test: every thread skips its N-th __syncthreads
+  int n_sync = 0;
+  void sync() {
+    if (++n_sync != NEUS_EMUL_DROP_BARRIER) pthread_barrier_wait(bar);
+  }
+#else
   void sync() { pthread_barrier_wait(bar); }
+#endif
   void cp16(void* dst, const void* src) { memcpy(dst, src, 16); }
   void cp_commit() {}
   void cp_wait_1() {}
@@ -73,7 +80,7 @@ extern "C" int neus_emul_forward(const neddf_neus_config_t* cfg, const float* co
   P.sdf = sdf; P.density = density; P.color = color; P.normal = normal;
   if (P.n <= 0) return 0;
   for (int blk = 0; blk < nblocks; ++blk) {
-    float* smem = (float*)aligned_alloc(64, (neus::kSmemBytes + 63) / 64 * 64);
+    float* smem = (float*)aligned_alloc(64, (neus::kSmemBytes + 63) / 64 * 64 + 64);
     for (int i = 0; i < neus::kSmemFloats; ++i) smem[i] = NAN;  // uninitialised shared memory must never be consumed
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, nullptr, neus::kThreads);
@@ -81,7 +88,11 @@ extern "C" int neus_emul_forward(const neddf_neus_config_t* cfg, const float* co
     for (int t = 0; t < neus::kThreads; ++t)
       th.emplace_back([&, t] {
         HostCtx cx{t, blk, nblocks, &bar};
+#ifdef NEUS_EMUL_MISALIGN  // negative control: shared memory base off by one float (a float4 access is then misaligned)
+        neus::tile_program(cx, P, smem + 1);
+#else
         neus::tile_program(cx, P, smem);
+#endif
       });
     for (auto& x : th) x.join();
     pthread_barrier_destroy(&bar);
