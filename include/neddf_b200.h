@@ -442,6 +442,39 @@ int32_t neddf_neus_forward_rays(const neddf_neus_t* h, const float* d_ray_dir, c
                                 int64_t n_rays, int32_t n_edges, int32_t sampling_type, float ray_radius, float* d_sdf,
                                 float* d_density, float* d_color, float* d_normal, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * NeRF field variant, training backward (the autograd graph of nerf.py:107-165 with respect to the parameters that
+ * nerf_trainer.py:38-42 hands to Adam).  fp32 CUDA-core kernel (csrc/nerf_train.cu + csrc/nerf_train_kernel.cuh): one
+ * launch recomputes the forward per 64-sample tile, walks back through the network and leaves the operands of the
+ * weight-gradient GEMMs in global memory; the gradients themselves are neddf_wgrad / neddf_colsum_value_rows calls on
+ * those buffers (what neddf_b200/nerf.py does).  STATUS: validated by the host emulation of its tile program only
+ * (tests/test_nerf_train_emul.py); opt-in in the Python layer until it has been run on hardware.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct neddf_nerf_train neddf_nerf_train_t; /* opaque: config + forward and transposed weight packs */
+
+int32_t neddf_nerf_train_create(const neddf_nerf_config_t* cfg, neddf_nerf_train_t** out);
+void neddf_nerf_train_destroy(neddf_nerf_train_t* h);
+/* Same arguments as neddf_nerf_set_weights. */
+int32_t neddf_nerf_train_set_weights(neddf_nerf_train_t* h, const float* const* d_w, const float* const* d_b, int32_t n_layers,
+                                     void* stream);
+
+/* Backward of NeRF.forward on n explicit samples.  Upstream gradients d_g_density [n], d_g_color [n,3].  Outputs, all
+ * fp32 row-major with the sample as the row: d_x [layer_count][n][256] hidden activations h_l, d_g [layer_count][n][256]
+ * gradients of the hidden pre-activations, d_e [n][6 embed_pos_rank] / d_d [n][6 embed_dir_rank] the embeddings,
+ * d_c1 / d_gc1 [n][256] activations / pre-activation gradients of outL_color.0 (columns >= 128 zero), d_gzd [n] gradient
+ * of the density pre-activation.  Then, with in_0 = E, in_l = [h_{l-1} | E if l-1 in skips]:
+ *   d layers.l.weight^T = in_l^T G_l, d layers.l.bias = colsum G_l, d outL_density.weight = GZD^T h_{L-1},
+ *   d outL_color.0.weight^T = [h_{L-1} | D]^T GC1, d outL_color.2.weight = g_color^T C1. */
+int32_t neddf_nerf_train_backward(const neddf_nerf_train_t* h, const float* lowpass, const float* d_pos, const float* d_dir,
+                                  const float* d_var, int64_t n, const float* d_g_density, const float* d_g_color, float* d_x,
+                                  float* d_g, float* d_e, float* d_d, float* d_c1, float* d_gc1, float* d_gzd, void* stream);
+/* Same with the sample geometry fused (rays [n_rays,3], dists [n_rays, n_edges]; n = n_rays * n_edges). */
+int32_t neddf_nerf_train_backward_rays(const neddf_nerf_train_t* h, const float* lowpass, const float* d_ray_dir,
+                                       const float* d_ray_orig, const float* d_dists, int64_t n_rays, int32_t n_edges,
+                                       int32_t sampling_type, float ray_radius, const float* d_g_density, const float* d_g_color,
+                                       float* d_x, float* d_g, float* d_e, float* d_d, float* d_c1, float* d_gc1, float* d_gzd,
+                                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

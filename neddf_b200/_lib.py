@@ -112,6 +112,11 @@ _SIGNATURES = {
     "neddf_nerf_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P]),
     "neddf_nerf_forward": (_I32, [_P, _FP, _P, _P, _P, _I64, _P, _P, _P]),
     "neddf_nerf_forward_rays": (_I32, [_P, _FP, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "neddf_nerf_train_create": (_I32, [C.POINTER(NerfConfig), C.POINTER(_P)]),
+    "neddf_nerf_train_destroy": (None, [_P]),
+    "neddf_nerf_train_set_weights": (_I32, [_P, C.POINTER(_P), C.POINTER(_P), _I32, _P]),
+    "neddf_nerf_train_backward": (_I32, [_P, _FP, _P, _P, _P, _I64] + [_P] * 9 + [_P]),
+    "neddf_nerf_train_backward_rays": (_I32, [_P, _FP, _P, _P, _P, _I64, _I32, _I32, _F] + [_P] * 9 + [_P]),
     "neddf_neus_layer_shapes": (_I32, [C.POINTER(NeusConfig), C.POINTER(C.c_int32), _I32]),
     "neddf_neus_create": (_I32, [C.POINTER(NeusConfig), C.POINTER(_P)]),
     "neddf_neus_destroy": (None, [_P]),

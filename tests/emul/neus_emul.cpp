@@ -5,42 +5,11 @@
 // grid a sequential loop over CTAs.  The build container has no GPU; this runs the kernel's own index arithmetic,
 // layer table, packing and barrier placement against the goldens.  CUDA intrinsics with one rounding are replaced by
 // the plain operation (-ffp-contract=off), libdevice sincosf / expf / tanhf by glibc's.
-#include <math.h>
-#include <pthread.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <thread>
-#include <vector>
-
-static inline float __fmul_rn(float a, float b) { return a * b; }
-static inline float __fadd_rn(float a, float b) { return a + b; }
-static inline float __fsub_rn(float a, float b) { return a - b; }
-static inline float __fdiv_rn(float a, float b) { return a / b; }
-static inline float __frcp_rn(float a) { return 1.0f / a; }
+#include "emul_common.h"
 
 #include "../../neddf_b200/csrc/neus_kernel.cuh"
 
 using namespace neddf;
-
-namespace {
-struct HostCtx {
-  int tid, block, nblocks;
-  pthread_barrier_t* bar;
-#ifdef NEUS_EMUL_DROP_BARRIER  // negative control of the sanitizer test: every thread skips its N-th __syncthreads
-  int n_sync = 0;
-  void sync() {
-    if (++n_sync != NEUS_EMUL_DROP_BARRIER) pthread_barrier_wait(bar);
-  }
-#else
-  void sync() { pthread_barrier_wait(bar); }
-#endif
-  void cp16(void* dst, const void* src) { memcpy(dst, src, 16); }
-  void cp_commit() {}
-  void cp_wait_1() {}
-  void cp_wait_0() {}
-};
-}  // namespace
 
 // Weights as torch stores them: w[i] = [out][in], b[i] = [out], in the order of neddf_neus_layer_shapes.
 // Explicit samples (pos / dir, n = samples) or rays (ray_dir / ray_orig / dists, n = rays).  Returns 0, or -1 for an
@@ -79,24 +48,11 @@ extern "C" int neus_emul_forward(const neddf_neus_config_t* cfg, const float* co
   }
   P.sdf = sdf; P.density = density; P.color = color; P.normal = normal;
   if (P.n <= 0) return 0;
-  for (int blk = 0; blk < nblocks; ++blk) {
-    float* smem = (float*)aligned_alloc(64, (neus::kSmemBytes + 63) / 64 * 64 + 64);
-    for (int i = 0; i < neus::kSmemFloats; ++i) smem[i] = NAN;  // uninitialised shared memory must never be consumed
-    pthread_barrier_t bar;
-    pthread_barrier_init(&bar, nullptr, neus::kThreads);
-    std::vector<std::thread> th;
-    for (int t = 0; t < neus::kThreads; ++t)
-      th.emplace_back([&, t] {
-        HostCtx cx{t, blk, nblocks, &bar};
 #ifdef NEUS_EMUL_MISALIGN  // negative control: shared memory base off by one float (a float4 access is then misaligned)
-        neus::tile_program(cx, P, smem + 1);
+  const int shift = 1;
 #else
-        neus::tile_program(cx, P, smem);
+  const int shift = 0;
 #endif
-      });
-    for (auto& x : th) x.join();
-    pthread_barrier_destroy(&bar);
-    free(smem);
-  }
+  emul::run_grid(nblocks, neus::kThreads, neus::kSmemFloats, shift, [&](emul::HostCtx& cx, float* smem) { neus::tile_program(cx, P, smem); });
   return 0;
 }
