@@ -121,14 +121,16 @@ class _NerfTrainFn(torch.autograd.Function):
             gwd = torch.empty(1, W, device=device, dtype=torch.float32)  # outL_density: GZD^T h_{L-1}
             wgrad_into(gwd, 0, GZD, 1, 1, X[Lh - 1], W)
             grads += [gwd, GZD.sum().reshape(1)]
-            gc1t = torch.empty(W + n_d, W // 2, device=device, dtype=torch.float32)  # outL_color.0: [h_{L-1} | D]^T GC1[:, :128]
-            wgrad_into(gc1t, 0, X[Lh - 1], W, W, GC1, W // 2)
-            wgrad_into(gc1t, W, D, n_d, n_d, GC1, W // 2)
-            grads += [gc1t.t().contiguous(), colsum(GC1)[:W // 2].contiguous()]
-            gc2 = torch.empty(3, W // 2, device=device, dtype=torch.float32)  # outL_color.2: g_color^T C1[:, :128]
+            # (all GEMMs with n_cols = ld_out = 256, the parameters test_wgrad_gemm holds on hardware; the colour branch is
+            #  128 wide, the upper half of GC1 / C1 is zero and sliced away)
+            gc1t = torch.empty(W + n_d, W, device=device, dtype=torch.float32)  # outL_color.0: [h_{L-1} | D]^T GC1
+            wgrad_into(gc1t, 0, X[Lh - 1], W, W, GC1, W)
+            wgrad_into(gc1t, W, D, n_d, n_d, GC1, W)
+            grads += [gc1t[:, :W // 2].t().contiguous(), colsum(GC1)[:W // 2].contiguous()]
+            gc2 = torch.empty(3, W, device=device, dtype=torch.float32)  # outL_color.2: g_color^T C1
             g_col2 = g_color.reshape(n, 3)
-            wgrad_into(gc2, 0, g_col2, 3, 3, C1, W // 2)
-            grads += [gc2, g_col2.sum(0)]
+            wgrad_into(gc2, 0, g_col2, 3, 3, C1, W)
+            grads += [gc2[:, :W // 2].contiguous(), g_col2.sum(0)]
         return (None, None, None, None, None, None) + tuple(grads)
 
 

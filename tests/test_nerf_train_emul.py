@@ -274,7 +274,7 @@ class _FakeLib:
         return 4096
 
     def neddf_wgrad(self, a, lda, a_col0, ka, b, ldb, rows, out, ld_out, n_cols, ws, stream):
-        assert 0 < ka <= 128 and 0 < n_cols <= 256 and ldb == 256  # the contract of include/neddf_b200.h
+        assert 0 < ka <= 128 and n_cols == 256 and ld_out == 256 and ldb == 256  # the parameters test_wgrad_gemm holds on hardware
         A = self._arr(a, rows * lda).reshape(rows, lda).astype(np.float64)
         B = self._arr(b, rows * ldb).reshape(rows, ldb).astype(np.float64)
         O = self._arr(out, (ka - 1) * ld_out + n_cols)
